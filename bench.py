@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""PFNL 4x forward benchmark: 4xSR HR-pixels/s on synthetic 7-frame 32x32 LR batches.
+
+    python bench.py --gpus N --steps K --warmup W          (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                   (the CPU restatement of the TF1 graph, rank 0 only)
+
+A step = one PFNL.forward over one batch of 16 clips x 7 x 32x32x3 per GPU (BASELINE.json
+configs[1]; weak scaling: N GPUs process N*16 clips, configs[2] at N=8).  Prints ONE JSON line.
+  value     device-resident forward (inputs already in HBM), CUDA events, max over ranks
+  e2e       the same metric through the public API with HOST buffers (H2D + forward + D2H per step)
+  roofline  dominant kernel, measured live with per-launch CUDA events (pfnl_profile) in a
+            separate K-step pass of the same workload
+  cpu_baseline  oracle (torch-CPU restatement, all host threads) on a bounded sample, rank 0, N=1
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+HR_PX_PER_CLIP = lambda h, w: (4 * h) * (4 * w)  # noqa: E731  (pixels, not x3 channels)
+METRIC = "4xSR HR-pixels/sec (PFNL forward, 7-frame 32x32 LR clips)"
+UNIT = "HR-pixels/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return {"hbm_gbs": float(d["hbm_gbs"]), "tensor_tflops": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    "tensor_tflops_burst": float(d["bf16_tflops"]), "source": "measured (MEASURED_PEAKS.json)"}
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "tensor_tflops": 1400.0, "tensor_tflops_burst": 1590.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 9:
+                self.rows.append(f)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for f in self.rows:
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # "under load" = samples within 25% of the highest clock seen (idle samples are excluded)
+        load = [s for s in sm if s >= 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_run(clips, size, steps, warmup, budget_s=None):
+    """Times the CPU restatement of the reference graph (oracle, torch-CPU back-end, all host
+    threads).  TensorFlow 1.12 itself cannot be installed in this image."""
+    import torch
+    from oracle import pfnl_ref as R
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    W = R.make_weights("A")
+    x = R.make_input(clips, size, size)
+    t0 = time.perf_counter()
+    R.pfnl_forward(x, W, backend="torch")
+    first = time.perf_counter() - t0
+    sample_clips = clips
+    if first > 3.0 and clips > 4:  # keep each step a bounded sample of the workload
+        sample_clips = 4
+        x = x[:sample_clips]
+    for _ in range(max(0, warmup - 1)):
+        R.pfnl_forward(x, W, backend="torch")
+    times = []
+    t_begin = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        R.pfnl_forward(x, W, backend="torch")
+        times.append(time.perf_counter() - t0)
+        if budget_s is not None and time.perf_counter() - t_begin > budget_s and len(times) >= 3:
+            break
+    mean_s = sum(times) / len(times)
+    value = sample_clips * HR_PX_PER_CLIP(size, size) / mean_s
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(times)} timed forwards of {sample_clips} clips x 7x{size}x{size} (torch-CPU/oneDNN fp32 "
+                      f"restatement of the TF1 graph, {cores} threads; TF 1.12 not installable)",
+            "ms_per_step": mean_s * 1e3, "steps": len(times)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    r = cpu_reference_run(args.clips, args.size, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"PFNL 4x forward, {args.clips} clips x 7x{args.size}x{args.size}x3 per step "
+                                   "(BASELINE configs[1] shape), CPU restatement of the TF1 graph",
+                       "clips_per_step": args.clips, "lr_size": args.size},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import torch
+    from pfnl_b200 import Engine, dist as D, weights as WT
+
+    rank, world, local = D.init_from_env()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: the CUDA path is the product, there is no CPU fallback")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    n_gpus = world
+    clips, size = args.clips, args.size
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    eng = Engine(WT.xavier_init(), device=local, precision=args.precision, graphs=not args.no_graphs)
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.rand((clips, 7, size, size, 3), generator=g, dtype=torch.float32).pin_memory()
+    out_host = torch.empty((clips, 1, 4 * size, 4 * size, 3), dtype=torch.float32).pin_memory()
+    x_dev = x_host.to(dev)
+    out_dev = torch.empty((clips, 1, 4 * size, 4 * size, 3), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+
+    for _ in range(Wm):
+        eng.forward(x_dev, out=out_dev)
+        eng.forward_host(x_host, out=out_host)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    # ---- device-resident steps ----------------------------------------------------------------
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    torch.cuda.synchronize()
+    l0 = eng.launches
+    wall0 = time.perf_counter()
+    for a, b in evs:
+        flush.zero_()
+        a.record()
+        eng.forward(x_dev, out=out_dev)
+        b.record()
+    torch.cuda.synchronize()
+    barrier()
+    wall_total = time.perf_counter() - wall0
+    launches = eng.launches - l0
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    ms_dev = D.max_over_ranks(sum(step_ms) / K, device=dev)
+
+    # ---- end to end through the public API with host buffers --------------------------------------
+    e2e_times = []
+    barrier()
+    for _ in range(K):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng.forward_host(x_host, out=out_host)   # H2D (pinned) + forward + D2H, returns when out_host is complete
+        e2e_times.append(time.perf_counter() - t0)
+    barrier()
+    ms_e2e = D.max_over_ranks(1e3 * sum(e2e_times) / K, device=dev)
+
+    # ---- per-kernel-class timing for the roofline (same workload, K steps) -----------------------
+    eng.profile(True)
+    for _ in range(K):
+        flush.zero_()
+        eng.forward(x_dev, out=out_dev)
+    prof = eng.profile_read()
+    eng.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        return 0
+
+    peaks = load_peaks()
+    hw = size * size
+    A_el = clips * 7 * hw * 64   # one 7-frame activation tensor (elements)
+    B_el = clips * hw * 64
+    tc = args.precision != "fp32"
+    act_bytes = 4                 # fp32 activations (fp16 hi+lo planes in fp16x3 are also 4 B/element)
+    if args.precision == "fp16":
+        act_bytes = 2
+    # algorithmic, layer-granular bytes per launch: conv1 2A, conv10 A+B, conv2+res 3A+B
+    # executed useful FLOPs per launch (the base/frame split of conv2 halves its K on the tensor-core path)
+    kinds = {
+        "conv1_3x3": {"bytes": 2 * A_el * act_bytes, "flops": 2.0 * clips * 7 * hw * 64 * 576},
+        "conv2_3x3": {"bytes": (3 * A_el + B_el) * act_bytes,
+                      "flops": 2.0 * clips * 7 * hw * 64 * (576 if tc else 1152)},
+        "conv10_1x1": {"bytes": (A_el + B_el) * act_bytes, "flops": 2.0 * clips * hw * 64 * 448},
+    }
+    prof_total = sum(v[0] for v in prof.values())
+    shares = {k: (v[0] / prof_total if prof_total > 0 else 0.0) for k, v in prof.items()}
+    dom = max(kinds, key=lambda k: prof[k][0])
+    dms, dcnt = prof[dom]
+    dur_s = dms / max(dcnt, 1) / 1e3
+    gbs = kinds[dom]["bytes"] / dur_s / 1e9 if dur_s > 0 else 0.0
+    tfl = kinds[dom]["flops"] / dur_s / 1e12 if dur_s > 0 else 0.0
+    roof_hbm = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": gbs / peaks["hbm_gbs"], "traffic": None}
+    roof_tensor = {"bound": "tensor", "achieved": tfl, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
+                   "frac": tfl / peaks["tensor_tflops"], "traffic": None}
+    roofline = dict(roof_tensor if (tc and roof_tensor["frac"] > roof_hbm["frac"]) else roof_hbm)
+    roofline.update({"kernel": dom, "avg_launch_ms": dms / max(dcnt, 1), "launches_timed": dcnt,
+                     "peak_source": peaks["source"], "algorithmic_bytes_per_launch": kinds[dom]["bytes"],
+                     "useful_flops_per_launch": kinds[dom]["flops"],
+                     "how": "CUDA events around each launch of this kernel class (pfnl_profile) on the launching "
+                            "stream, K steps of the same workload, L2 flushed between steps",
+                     "other": roof_hbm if roofline_is(roof_tensor, tc, roof_hbm) else roof_tensor,
+                     "share_of_step": shares.get(dom)})
+    if not tc:
+        roofline["note"] = ("fp32 parity path: this kernel is FFMA-bound (%.1f TFLOP/s fp32 on CUDA cores), "
+                            "not HBM-bound" % tfl)
+
+    total_clips = clips * n_gpus
+    value = total_clips * HR_PX_PER_CLIP(size, size) / (ms_dev / 1e3)
+    e2e_value = total_clips * HR_PX_PER_CLIP(size, size) / (ms_e2e / 1e3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "fp16x3": "f32 (3x fp16-split tcgen05, fp32 accumulate)",
+                  "fp16": "f16 operands, f32 accumulate"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": f"PFNL 4x forward, batch={clips} clips x 7x{size}x{size}x3 per GPU "
+                               f"(BASELINE configs[1]; {total_clips} clips over {n_gpus} GPU(s))",
+                   "clips_per_gpu": clips, "global_batch": total_clips, "lr_size": size,
+                   "precision": args.precision, "weights": "Xavier-uniform seed 4321 (reference init, no checkpoint)",
+                   "parallelism": f"clip-sharded dp{n_gpus}", "cuda_graphs": not args.no_graphs,
+                   "l2": "256 MiB buffer written between timed steps (L2 flush)",
+                   "timing": "per-step CUDA events on the launching stream, mean over K, max over ranks"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4),
+                "how": "pfnl_forward_host via Engine.forward_host: pinned host LR -> device, forward, SR -> pinned host"},
+        "gpu_launches": int(launches),
+        "launches_per_step": launches / K,
+        "wall_s_timed_region": wall_total,
+        "roofline": roofline,
+        "kernel_ms_per_step": {k: v[0] / K for k, v in prof.items() if v[1]},
+        "clocks": clocks,
+    }
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(clips, size, steps=10, warmup=1, budget_s=args.cpu_seconds)
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def roofline_is(roof_tensor, tc, roof_hbm):
+    return tc and roof_tensor["frac"] > roof_hbm["frac"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("PFNL_BENCH_PRECISION", "fp32"),
+                    choices=["fp32", "fp16x3", "fp16"])
+    ap.add_argument("--clips", type=int, default=16, help="clips per GPU per step")
+    ap.add_argument("--size", type=int, default=32, help="LR frame size")
+    ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,170 @@
+/* pfnl_b200.h - C ABI of libpfnl_b200.so: the B200 (sm_100a) implementation of the PFNL
+ * 4x multi-frame forward hot path.
+ *
+ * The reference (psychopa4/PFNL, TensorFlow 1.12, pure Python) has no FFI; the seam this
+ * library plugs into is the Python method boundary PFNL.forward(x) and its call sites
+ *     sr = sess.run(SR_test, feed_dict={L_test: batch})      model/pfnl.py:252, :309
+ *     mse_val = sess.run(self.eval_mse, feed_dict={...})      model/pfnl.py:130 (graph :90)
+ * Each entry point below names the reference code it replaces.  Plain pointers and sizes
+ * only - no torch / TF types.  All tensors are fp32, channels-last, contiguous.
+ *
+ * Conventions
+ *   - every function returns PFNL_OK (0) or a negative pfnl_status; the message for the
+ *     calling thread's last failure is pfnl_last_error().
+ *   - "dev" pointers are CUDA device pointers on the handle's device, "host" pointers are
+ *     ordinary host memory.  `stream` is a cudaStream_t passed as void* (NULL = default
+ *     stream).  Calls are asynchronous on `stream` unless stated otherwise.
+ *   - the caller owns every I/O buffer and keeps it alive until the stream has drained.
+ *   - a handle is bound to one device and is not thread-safe; distinct handles are
+ *     independent.  There is NO CPU fallback: on a device that is not sm_100 every compute
+ *     entry point returns PFNL_ERR_UNSUPPORTED_ARCH.
+ */
+#ifndef PFNL_B200_H
+#define PFNL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFNL_VERSION 100 /* 0.1.0 */
+
+#define PFNL_NUM_FRAMES 7  /* model/pfnl.py:22 */
+#define PFNL_SCALE 4       /* model/pfnl.py:23 */
+#define PFNL_NUM_BLOCK 20  /* model/pfnl.py:43 */
+#define PFNL_MF 64         /* model/pfnl.py:40 */
+#define PFNL_NL_CH 84      /* 3*7*4, model/pfnl.py:58 */
+
+typedef enum pfnl_status {
+  PFNL_OK = 0,
+  PFNL_ERR_BAD_ARG = -1,          /* NULL pointer, unknown enum value */
+  PFNL_ERR_BAD_SHAPE = -2,        /* odd H/W (tf.space_to_depth needs even, pfnl.py:57), N<=0 ... */
+  PFNL_ERR_CUDA = -3,             /* a CUDA runtime/driver call failed */
+  PFNL_ERR_UNSUPPORTED_ARCH = -4, /* device is not compute capability 10.x */
+  PFNL_ERR_UNIMPLEMENTED = -5,
+  PFNL_ERR_NO_MEMORY = -6
+} pfnl_status;
+
+/* Arithmetic used by the conv / non-local kernels.  Reorders are index-exact in all modes. */
+typedef enum pfnl_precision {
+  PFNL_PREC_FP32 = 0,       /* FFMA everywhere: the <=1e-3 parity path */
+  PFNL_PREC_TC_FP16X3 = 1,  /* tcgen05 convs on hi/lo-split fp16 operands (3 MMAs, fp32 accumulate) */
+  PFNL_PREC_TC_FP16 = 2     /* tcgen05 convs + tcgen05 non-local block on fp16 operands, fp32 accumulate */
+} pfnl_precision;
+
+/* Weights, HOST pointers, TF layouts (kernels HWIO [kh,kw,Cin,Cout], biases [Cout]).
+ * Field <-> TF variable (scope 'nlvsr', model/pfnl.py:47-53; utils.py:23-26,66-67):
+ *   nl_g_*      nlvsr/nlblock_0/g/g/{kernel,bias}   [1,1,84,84],[84]
+ *   nl_w_*      nlvsr/nlblock_0/w/w/{kernel,bias}   [1,1,84,84],[84]
+ *   conv0_*     nlvsr/conv0/{kernel,bias}           [5,5,3,64],[64]
+ *   conv1_*[i]  nlvsr/conv1_{i}/...                 [3,3,64,64],[64]
+ *   conv10_*[i] nlvsr/conv10_{i}/...                [1,1,448,64],[64]  (Cin = t*64+c, pfnl.py:67)
+ *   conv2_*[i]  nlvsr/conv2_{i}/...                 [3,3,128,64],[64]  (Cin 0-63 base, 64-127 frame, pfnl.py:69)
+ *   merge1_*    nlvsr/convmerge1/...                [3,3,448,48],[48]
+ *   merge2_*    nlvsr/convmerge2/...                [3,3,12,12],[12]
+ * pfnl_create copies and repacks them; the caller may free them afterwards. */
+typedef struct pfnl_weights {
+  const float* nl_g_kernel;
+  const float* nl_g_bias;
+  const float* nl_w_kernel;
+  const float* nl_w_bias;
+  const float* conv0_kernel;
+  const float* conv0_bias;
+  const float* conv1_kernel[PFNL_NUM_BLOCK];
+  const float* conv1_bias[PFNL_NUM_BLOCK];
+  const float* conv10_kernel[PFNL_NUM_BLOCK];
+  const float* conv10_bias[PFNL_NUM_BLOCK];
+  const float* conv2_kernel[PFNL_NUM_BLOCK];
+  const float* conv2_bias[PFNL_NUM_BLOCK];
+  const float* merge1_kernel;
+  const float* merge1_bias;
+  const float* merge2_kernel;
+  const float* merge2_bias;
+} pfnl_weights;
+
+typedef struct pfnl_handle pfnl_handle;
+
+int pfnl_version(void);
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* pfnl_last_error(void);
+/* 1 if `device` is compute capability 10.x, 0 if not, negative status on error. */
+int pfnl_device_supported(int device);
+
+/* Replaces: graph construction + variable initialisation/restore in test_video_*
+ * (model/pfnl.py:220-232, 281-291): builds the per-device state for PFNL.forward. */
+int pfnl_create(pfnl_handle** out, int device, const pfnl_weights* weights, int precision);
+int pfnl_destroy(pfnl_handle* h);
+
+/* Bytes of device workspace pfnl_forward needs for a batch of N clips of HxW LR frames. */
+size_t pfnl_workspace_bytes(int precision, int N, int H, int W);
+/* Pre-allocates the workspace for (N,H,W) so that pfnl_forward does not allocate
+ * (and can be captured in a CUDA graph).  Synchronous. */
+int pfnl_reserve(pfnl_handle* h, int N, int H, int W);
+/* 1: pfnl_forward replays a cached CUDA graph per (N,H,W) shape; 0: plain launches. */
+int pfnl_set_graphs(pfnl_handle* h, int enable);
+
+/* Replaces: sess.run(SR_test, feed_dict={L_test: lr}) -> PFNL.forward, model/pfnl.py:39-80.
+ *   lr_dev [N,7,H,W,3] -> sr_dev [N,1,4H,4W,3]; H and W even. */
+int pfnl_forward(pfnl_handle* h, const float* lr_dev, int N, int H, int W, float* sr_dev,
+                 void* stream);
+/* Same call with HOST buffers, mirroring the feed/fetch of model/pfnl.py:251-253: copies
+ * lr to the device (through pinned staging), runs the forward, copies sr back, and
+ * returns when sr_host is complete. */
+int pfnl_forward_host(pfnl_handle* h, const float* lr_host, int N, int H, int W, float* sr_host,
+                      void* stream);
+
+/* Replaces: eval_mse = tf.reduce_mean((SR-H)**2, axis=[2,3,4]), model/pfnl.py:90.
+ *   sr_dev, hr_dev [N,1,H4,W4,3] -> mse_dev [N]. */
+int pfnl_mse(pfnl_handle* h, const float* sr_dev, const float* hr_dev, int N, int H4, int W4,
+             float* mse_dev, void* stream);
+
+/* Kernel launches issued by this handle since creation (graph replays count their nodes). */
+long long pfnl_launch_count(const pfnl_handle* h);
+
+/* Per-kernel-class device timing for roofline reporting.  pfnl_profile(h,1) makes every
+ * following pfnl_forward bracket its launches with CUDA events on the launching stream (CUDA
+ * graphs are bypassed while it is on); pfnl_profile_read synchronises the device, returns the
+ * summed milliseconds and launch counts per class since the last read, and resets them.
+ * Classes (PFNL_PROF_KINDS = 9): 0 pack_tokens, 1 non-local, 2 conv0, 3 conv1 (3x3 64->64),
+ * 4 conv10 (1x1 448->64), 5 conv2 (3x3 128->64 + residual), 6 convmerge1, 7 tail, 8 other. */
+#define PFNL_PROF_KINDS 9
+int pfnl_profile(pfnl_handle* h, int enable);
+int pfnl_profile_read(pfnl_handle* h, double* ms_by_kind, long long* launches_by_kind);
+
+/* ---- stage-level entry points (isolation benchmarks and parity tests) ---------------- */
+
+/* tf.concat(frames,-1) + tf.space_to_depth(.,2), model/pfnl.py:55-57:
+ *   lr [N,7,H,W,3] -> tokens [N,(H/2)*(W/2),84], channel = (dy*2+dx)*21 + t*3 + c. */
+int pfnl_pack_tokens(pfnl_handle* h, const float* lr_dev, int N, int H, int W, float* tokens_dev,
+                     void* stream);
+/* NonLocalBlock(nltype=1, sub_sample=1), utils.py:18-71: tokens [N,L,84] -> [N,L,84]. */
+int pfnl_nonlocal(pfnl_handle* h, const float* tokens_dev, int N, int L, float* out_dev,
+                  void* stream);
+/* tf.depth_to_space (DCR), model/pfnl.py:59,76,78 == modules/ps.py:_PS:
+ *   in [N,H,W,C] -> out [N,H*b,W*b,C/(b*b)]. */
+int pfnl_depth_to_space(pfnl_handle* h, const float* in_dev, int N, int H, int W, int C, int block,
+                        float* out_dev, void* stream);
+/* tf.space_to_depth, model/pfnl.py:57: in [N,H,W,C] -> out [N,H/b,W/b,C*b*b]. */
+int pfnl_space_to_depth(pfnl_handle* h, const float* in_dev, int N, int H, int W, int C, int block,
+                        float* out_dev, void* stream);
+/* tf.layers.Conv2D(strides=1,padding='same') NHWC/HWIO, model/pfnl.py:48-53:
+ *   in [N,H,W,Cin], kernel [k,k,Cin,Cout] (device), bias [Cout] (device),
+ *   optional residual [N,H,W,Cout] added after the activation (model/pfnl.py:71),
+ *   act: 0 none, 1 leaky_relu(0.2).  k in {1,3,5}.  Always fp32 FFMA. */
+int pfnl_conv2d_nhwc(pfnl_handle* h, const float* in_dev, int N, int H, int W, int Cin,
+                     const float* kernel_dev, const float* bias_dev, int k, int Cout, int act,
+                     const float* residual_dev, float* out_dev, void* stream);
+/* tf.image.resize_images(img,[4H,4W],method=2), model/pfnl.py:63: [N,H,W,C] -> [N,4H,4W,C]. */
+int pfnl_bicubic4(pfnl_handle* h, const float* in_dev, int N, int H, int W, int C, float* out_dev,
+                  void* stream);
+/* One Progressive Fusion Residual Block (model/pfnl.py:66-71) with block index `blk`'s
+ * weights, in the handle's precision: frames [N*7,H,W,64] fp32 -> frames_out (may alias). */
+int pfnl_pfrb(pfnl_handle* h, int blk, const float* frames_dev, int N, int H, int W,
+              float* frames_out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFNL_B200_H */

@@ -1,0 +1,98 @@
+"""In-tree build of libpfnl_b200.so for sm_100a (nvcc cross-compiles without a GPU).
+
+    python -m pfnl_b200.build [--force] [--verbose]
+
+The shared library is written next to this file so that it travels to the GPU box with the
+repo snapshot (built artefacts are git-ignored, not gpurun-ignored).
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libpfnl_b200.so")
+
+SOURCES = ["api.cu", "reorder.cu", "conv_ffma.cu", "nonlocal_ffma.cu", "mse.cu", "tc_stub.cu"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: libpfnl_b200.so cannot be built")
+
+
+def _digest(paths):
+    h = hashlib.sha256()
+    for p in sorted(paths):
+        h.update(p.encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    os.makedirs(BUILD, exist_ok=True)
+    nvcc = _nvcc()
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    deps.append(os.path.join(HERE, "..", "include", "pfnl_b200.h"))
+    deps.append(os.path.abspath(__file__))
+    stamp = os.path.join(BUILD, "stamp.txt")
+    dig = _digest([os.path.abspath(d) for d in deps])
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        return LIB
+
+    def compile_one(src):
+        obj = os.path.join(BUILD, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, r
+
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    log = []
+    objs = []
+    for src, obj, r in results:
+        log.append(f"==== {src} (rc={r.returncode})\n{r.stdout}{r.stderr}")
+        if r.returncode != 0:
+            sys.stderr.write(log[-1])
+            raise RuntimeError(f"nvcc failed on {src}")
+        objs.append(obj)
+    with open(os.path.join(BUILD, "ptxas.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+           "-cudart", "static"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    with open(stamp, "w") as f:
+        f.write(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    a = ap.parse_args()
+    print(build(force=a.force, verbose=a.verbose))

@@ -1,0 +1,784 @@
+// C ABI of libpfnl_b200.so (include/pfnl_b200.h): handle, workspace, the PFNL.forward launch
+// sequence (model/pfnl.py:39-80) and the stage-level entry points.
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tc.h"
+
+namespace pfnl {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return PFNL_ERR_CUDA;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+  // fp32 path
+  float* tokens;   // [N,L,84]
+  float* g;        // [N,L,84]
+  float* yatt;     // [N,L,84]
+  float* inp21;    // [N,H,W,21]
+  float* framesA;  // [N*7,H,W,64]  inp0 (residual stream)
+  float* framesB;  // [N*7,H,W,64]  inp1
+  float* base;     // [N,H,W,64]
+  float* merge;    // [N,H,W,48]
+  TcWorkspace tc;  // tensor-core path buffers (precision 1,2)
+  size_t bytes;
+};
+
+// Lays the workspace out behind `base` (may be NULL to only size it).
+static Workspace carve(char* basep, int precision, int N, int H, int W) {
+  Workspace w;
+  memset(&w, 0, sizeof(w));
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> char* {
+    char* p = basep ? basep + off : nullptr;
+    off += align_up(bytes, 1024);
+    return p;
+  };
+  const size_t L = (size_t)(H / 2) * (W / 2);
+  const size_t hw = (size_t)H * W;
+  w.tokens = (float*)take((size_t)N * L * kNL * 4);
+  w.g = (float*)take((size_t)N * L * kNL * 4);
+  w.yatt = (float*)take((size_t)N * L * kNL * 4);
+  w.inp21 = (float*)take((size_t)N * hw * 21 * 4);
+  w.framesA = (float*)take((size_t)N * kFrames * hw * kMF * 4);
+  w.framesB = (float*)take((size_t)N * kFrames * hw * kMF * 4);
+  w.base = (float*)take((size_t)N * hw * kMF * 4);
+  w.merge = (float*)take((size_t)N * hw * 48 * 4);
+  if (precision != PFNL_PREC_FP32) tc_carve(w.tc, precision, N, H, W, take);
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace pfnl
+
+using namespace pfnl;
+
+struct pfnl_handle {
+  int device = -1;
+  int precision = 0;
+  // raw HWIO weights on the device (fp32)
+  float *nl_g_w = nullptr, *nl_g_b = nullptr, *nl_w_w = nullptr, *nl_w_b = nullptr;
+  float *conv0_w = nullptr, *conv0_b = nullptr;
+  float* conv1_w[PFNL_NUM_BLOCK] = {};
+  float* conv1_b[PFNL_NUM_BLOCK] = {};
+  float* conv10_w[PFNL_NUM_BLOCK] = {};
+  float* conv10_b[PFNL_NUM_BLOCK] = {};
+  float* conv2_w[PFNL_NUM_BLOCK] = {};
+  float* conv2_b[PFNL_NUM_BLOCK] = {};
+  float *merge1_w = nullptr, *merge1_b = nullptr, *merge2_w = nullptr, *merge2_b = nullptr;
+  // FFMA-packed kernels
+  float* conv1_p[PFNL_NUM_BLOCK] = {};
+  float* conv10_p[PFNL_NUM_BLOCK] = {};
+  float* conv2_p[PFNL_NUM_BLOCK] = {};
+  float* merge1_p = nullptr;
+  TcWeights tcw;  // tensor-core packed kernels (precision 1,2)
+  std::vector<void*> allocs;
+  // workspace
+  char* ws = nullptr;
+  size_t ws_cap = 0;
+  double* mse_partial = nullptr;
+  int mse_cap = 0;
+  // scratch for pfnl_conv2d_nhwc's on-the-fly weight packing
+  float* pack_scratch = nullptr;
+  size_t pack_cap = 0;
+  // host staging for pfnl_forward_host
+  float *pin_in = nullptr, *pin_out = nullptr, *dev_in = nullptr, *dev_out = nullptr;
+  size_t pin_in_cap = 0, pin_out_cap = 0;
+  long long launches = 0;
+  Profiler prof;
+  bool graphs = false;
+  std::map<std::tuple<int, int, int, const void*, void*>, cudaGraphExec_t> graph_cache;
+  std::map<std::tuple<int, int, int, const void*, void*>, long long> graph_nodes;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+int upload(pfnl_handle* h, const float* host, size_t n, float** out) {
+  if (!host) {
+    set_error("pfnl_create: a weight pointer is NULL");
+    return PFNL_ERR_BAD_ARG;
+  }
+  float* d = nullptr;
+  PFNL_CUDA(cudaMalloc(&d, n * sizeof(float)));
+  h->allocs.push_back(d);
+  PFNL_CUDA(cudaMemcpy(d, host, n * sizeof(float), cudaMemcpyHostToDevice));
+  *out = d;
+  return PFNL_OK;
+}
+
+int dev_alloc(pfnl_handle* h, size_t bytes, void** out) {
+  void* d = nullptr;
+  PFNL_CUDA(cudaMalloc(&d, bytes));
+  h->allocs.push_back(d);
+  *out = d;
+  return PFNL_OK;
+}
+
+int check_shape(int N, int H, int W) {
+  if (N <= 0 || H <= 0 || W <= 0) {
+    set_error("bad shape N=%d H=%d W=%d (must be positive)", N, H, W);
+    return PFNL_ERR_BAD_SHAPE;
+  }
+  if ((H & 1) || (W & 1)) {
+    set_error("bad shape H=%d W=%d: tf.space_to_depth(.,2) needs even H and W (model/pfnl.py:57)", H, W);
+    return PFNL_ERR_BAD_SHAPE;
+  }
+  return PFNL_OK;
+}
+
+int ensure_workspace(pfnl_handle* h, int N, int H, int W) {
+  const size_t need = carve(nullptr, h->precision, N, H, W).bytes;
+  if (need <= h->ws_cap) return PFNL_OK;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (h->ws) {
+    PFNL_CUDA(cudaDeviceSynchronize());
+    for (auto& kv : h->graph_cache) cudaGraphExecDestroy(kv.second);
+    h->graph_cache.clear();
+    h->graph_nodes.clear();
+    PFNL_CUDA(cudaFree(h->ws));
+    h->ws = nullptr;
+    h->ws_cap = 0;
+  }
+  (void)st;
+  cudaError_t e = cudaMalloc((void**)&h->ws, need);
+  if (e != cudaSuccess) {
+    set_error("workspace allocation of %zu bytes failed: %s", need, cudaGetErrorString(e));
+    cudaGetLastError();
+    return PFNL_ERR_NO_MEMORY;
+  }
+  h->ws_cap = need;
+  return PFNL_OK;
+}
+
+ConvSlice make_slice(const float* p, long long img_stride, int img_div, int pix_stride) {
+  ConvSlice s;
+  s.ptr = p;
+  s.img_stride = img_stride;
+  s.img_div = img_div;
+  s.pix_stride = pix_stride;
+  return s;
+}
+
+// One Progressive Fusion Residual Block on the fp32 path (model/pfnl.py:66-71).
+int pfrb_fp32(pfnl_handle* h, int i, const float* in, float* out, Workspace& w, int N, int H, int W,
+              cudaStream_t s) {
+  const long long hw = (long long)H * W;
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.H = H;
+  a.W = W;
+  a.act = 1;
+  a.cout = kMF;
+  // inp1[t] = conv1_i(inp0[t])                              pfnl.py:66
+  a.nslices = 1;
+  a.slice_ch = kMF;
+  a.slice[0] = make_slice(in, hw * kMF, 1, kMF);
+  a.images = N * kFrames;
+  a.wpack = h->conv1_p[i];
+  a.bias = h->conv1_b[i];
+  a.residual = nullptr;
+  a.out = w.framesB;
+  h->prof.begin(kProfConv1, s);
+  int rc = launch_conv_ffma(3, a, s);
+  h->prof.end(s);
+  if (rc) return rc;
+  // base = conv10_i(concat_t inp1[t])                       pfnl.py:67-68
+  a.nslices = kFrames;
+  for (int t = 0; t < kFrames; ++t) a.slice[t] = make_slice(w.framesB + t * hw * kMF, kFrames * hw * kMF, 1, kMF);
+  a.images = N;
+  a.wpack = h->conv10_p[i];
+  a.bias = h->conv10_b[i];
+  a.out = w.base;
+  h->prof.begin(kProfConv10, s);
+  rc = launch_conv_ffma(1, a, s);
+  h->prof.end(s);
+  if (rc) return rc;
+  // inp0[t] += conv2_i(concat[base, inp1[t]])               pfnl.py:69-71
+  a.nslices = 2;
+  a.slice[0] = make_slice(w.base, hw * kMF, kFrames, kMF);
+  a.slice[1] = make_slice(w.framesB, hw * kMF, 1, kMF);
+  a.images = N * kFrames;
+  a.wpack = h->conv2_p[i];
+  a.bias = h->conv2_b[i];
+  a.residual = in;
+  a.out = out;
+  h->prof.begin(kProfConv2, s);
+  rc = launch_conv_ffma(3, a, s);
+  h->prof.end(s);
+  if (rc) return rc;
+  h->launches += 3;
+  return PFNL_OK;
+}
+
+int forward_launches(pfnl_handle* h, const float* lr, int N, int H, int W, float* sr, cudaStream_t s) {
+  Workspace w = carve(h->ws, h->precision, N, H, W);
+  const int L = (H / 2) * (W / 2);
+  const long long hw = (long long)H * W;
+  int rc;
+  // tokens = space_to_depth(concat frames)                  pfnl.py:55-57
+  h->prof.begin(kProfPack, s);
+  rc = launch_pack_tokens(lr, N, H, W, w.tokens, s);
+  h->prof.end(s);
+  if (rc) return rc;
+  h->launches += 1;
+  if (h->precision == PFNL_PREC_TC_FP16) {
+    if ((rc = tc_nonlocal(h->tcw, w.tc, w.tokens, lr, N, H, W, w.inp21, s, &h->launches, &h->prof))) return rc;
+  } else {
+    h->prof.begin(kProfNonlocal, s);
+    // NonLocalBlock                                         pfnl.py:58, utils.py:18-71
+    if ((rc = launch_nl_linear(w.tokens, N * L, h->nl_g_w, h->nl_g_b, w.g, s))) return rc;
+    if ((rc = launch_nl_flash_ffma(w.tokens, w.g, N, L, w.yatt, s))) return rc;
+    // inp0 += depth_to_space(w(y))                          pfnl.py:59-60
+    if ((rc = launch_nl_linear_scatter(w.yatt, lr, N, H, W, h->nl_w_w, h->nl_w_b, w.inp21, s))) return rc;
+    h->prof.end(s);
+    h->launches += 3;
+  }
+  if (h->precision == PFNL_PREC_FP32) {
+    // conv0 on each frame                                   pfnl.py:61-62
+    h->prof.begin(kProfConv0, s);
+    rc = launch_conv0(w.inp21, N, H, W, h->conv0_w, h->conv0_b, w.framesA, s);
+    h->prof.end(s);
+    if (rc) return rc;
+    h->launches += 1;
+    for (int i = 0; i < PFNL_NUM_BLOCK; ++i)
+      if ((rc = pfrb_fp32(h, i, w.framesA, w.framesA, w, N, H, W, s))) return rc;
+    // merge = convmerge1(concat_t inp0[t])                  pfnl.py:73-74
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.H = H;
+    a.W = W;
+    a.act = 1;
+    a.cout = 48;
+    a.nslices = kFrames;
+    a.slice_ch = kMF;
+    for (int t = 0; t < kFrames; ++t) a.slice[t] = make_slice(w.framesA + t * hw * kMF, kFrames * hw * kMF, 1, kMF);
+    a.images = N;
+    a.wpack = h->merge1_p;
+    a.bias = h->merge1_b;
+    a.out = w.merge;
+    h->prof.begin(kProfMerge1, s);
+    rc = launch_conv_ffma(3, a, s);
+    h->prof.end(s);
+    if (rc) return rc;
+    h->launches += 1;
+  } else {
+    if ((rc = tc_trunk(h->tcw, w.tc, h->precision, w.inp21, N, H, W, w.merge, s, &h->launches, &h->prof))) return rc;
+  }
+  // depth_to_space -> convmerge2 -> depth_to_space, + bicubic skip    pfnl.py:63,76-80
+  h->prof.begin(kProfTail, s);
+  rc = launch_tail(w.merge, lr, N, H, W, h->merge2_w, h->merge2_b, sr, s);
+  h->prof.end(s);
+  if (rc) return rc;
+  h->launches += 1;
+  return PFNL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pfnl_version(void) { return PFNL_VERSION; }
+
+const char* pfnl_last_error(void) { return g_err; }
+
+int pfnl_device_supported(int device) {
+  cudaDeviceProp p;
+  cudaError_t e = cudaGetDeviceProperties(&p, device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties", __FILE__, __LINE__);
+  return p.major == 10 ? 1 : 0;
+}
+
+int pfnl_create(pfnl_handle** out, int device, const pfnl_weights* wts, int precision) {
+  if (!out || !wts) {
+    set_error("pfnl_create: NULL argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  *out = nullptr;
+  if (precision < PFNL_PREC_FP32 || precision > PFNL_PREC_TC_FP16) {
+    set_error("pfnl_create: unknown precision %d", precision);
+    return PFNL_ERR_BAD_ARG;
+  }
+  int sup = pfnl_device_supported(device);
+  if (sup < 0) return sup;
+  if (sup == 0) {
+    set_error("pfnl_create: device %d is not compute capability 10.x (sm_100a only, no fallback)", device);
+    return PFNL_ERR_UNSUPPORTED_ARCH;
+  }
+  DeviceGuard guard(device);
+  if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
+  pfnl_handle* h = new pfnl_handle();
+  h->device = device;
+  h->precision = precision;
+  int rc = PFNL_OK;
+#define TRY(x)              \
+  do {                      \
+    if ((rc = (x))) goto fail; \
+  } while (0)
+  TRY(init_conv_ffma());
+  TRY(init_nonlocal_ffma());
+  TRY(upload(h, wts->nl_g_kernel, kNL * kNL, &h->nl_g_w));
+  TRY(upload(h, wts->nl_g_bias, kNL, &h->nl_g_b));
+  TRY(upload(h, wts->nl_w_kernel, kNL * kNL, &h->nl_w_w));
+  TRY(upload(h, wts->nl_w_bias, kNL, &h->nl_w_b));
+  TRY(upload(h, wts->conv0_kernel, 75 * 64, &h->conv0_w));
+  TRY(upload(h, wts->conv0_bias, 64, &h->conv0_b));
+  for (int i = 0; i < PFNL_NUM_BLOCK; ++i) {
+    TRY(upload(h, wts->conv1_kernel[i], 9 * 64 * 64, &h->conv1_w[i]));
+    TRY(upload(h, wts->conv1_bias[i], 64, &h->conv1_b[i]));
+    TRY(upload(h, wts->conv10_kernel[i], 448 * 64, &h->conv10_w[i]));
+    TRY(upload(h, wts->conv10_bias[i], 64, &h->conv10_b[i]));
+    TRY(upload(h, wts->conv2_kernel[i], 9 * 128 * 64, &h->conv2_w[i]));
+    TRY(upload(h, wts->conv2_bias[i], 64, &h->conv2_b[i]));
+  }
+  TRY(upload(h, wts->merge1_kernel, 9 * 448 * 48, &h->merge1_w));
+  TRY(upload(h, wts->merge1_bias, 48, &h->merge1_b));
+  TRY(upload(h, wts->merge2_kernel, 9 * 12 * 12, &h->merge2_w));
+  TRY(upload(h, wts->merge2_bias, 12, &h->merge2_b));
+  // FFMA packing (used by precision 0 and by pfnl_pfrb/pfnl_conv2d_nhwc reference launches)
+  for (int i = 0; i < PFNL_NUM_BLOCK; ++i) {
+    TRY(dev_alloc(h, conv_ffma_packed_floats(3, 64) * 4, (void**)&h->conv1_p[i]));
+    TRY(launch_pack_conv_ffma_weights(h->conv1_w[i], 3, 64, 64, h->conv1_p[i], 0));
+    TRY(dev_alloc(h, conv_ffma_packed_floats(1, 448) * 4, (void**)&h->conv10_p[i]));
+    TRY(launch_pack_conv_ffma_weights(h->conv10_w[i], 1, 448, 64, h->conv10_p[i], 0));
+    TRY(dev_alloc(h, conv_ffma_packed_floats(3, 128) * 4, (void**)&h->conv2_p[i]));
+    TRY(launch_pack_conv_ffma_weights(h->conv2_w[i], 3, 128, 64, h->conv2_p[i], 0));
+  }
+  TRY(dev_alloc(h, conv_ffma_packed_floats(3, 448) * 4, (void**)&h->merge1_p));
+  TRY(launch_pack_conv_ffma_weights(h->merge1_w, 3, 448, 48, h->merge1_p, 0));
+  if (precision != PFNL_PREC_FP32) {
+    TcRawWeights raw;
+    raw.nl_g_w = h->nl_g_w;
+    raw.nl_g_b = h->nl_g_b;
+    raw.nl_w_w = h->nl_w_w;
+    raw.nl_w_b = h->nl_w_b;
+    raw.conv0_w = h->conv0_w;
+    raw.conv0_b = h->conv0_b;
+    for (int i = 0; i < PFNL_NUM_BLOCK; ++i) {
+      raw.conv1_w[i] = h->conv1_w[i];
+      raw.conv1_b[i] = h->conv1_b[i];
+      raw.conv10_w[i] = h->conv10_w[i];
+      raw.conv10_b[i] = h->conv10_b[i];
+      raw.conv2_w[i] = h->conv2_w[i];
+      raw.conv2_b[i] = h->conv2_b[i];
+    }
+    raw.merge1_w = h->merge1_w;
+    raw.merge1_b = h->merge1_b;
+    TRY(tc_init(h->tcw, precision, raw, h->allocs));
+  }
+  {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      rc = cuda_fail(e, "cudaDeviceSynchronize", __FILE__, __LINE__);
+      goto fail;
+    }
+  }
+#undef TRY
+  *out = h;
+  return PFNL_OK;
+fail:
+  pfnl_destroy(h);
+  return rc;
+}
+
+int pfnl_destroy(pfnl_handle* h) {
+  if (!h) return PFNL_OK;
+  DeviceGuard guard(h->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : h->graph_cache) cudaGraphExecDestroy(kv.second);
+  for (auto& r : h->prof.recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  for (auto e : h->prof.pool) cudaEventDestroy(e);
+  tc_destroy(h->tcw);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->ws) cudaFree(h->ws);
+  if (h->mse_partial) cudaFree(h->mse_partial);
+  if (h->pack_scratch) cudaFree(h->pack_scratch);
+  if (h->pin_in) cudaFreeHost(h->pin_in);
+  if (h->pin_out) cudaFreeHost(h->pin_out);
+  if (h->dev_in) cudaFree(h->dev_in);
+  if (h->dev_out) cudaFree(h->dev_out);
+  cudaGetLastError();
+  delete h;
+  return PFNL_OK;
+}
+
+size_t pfnl_workspace_bytes(int precision, int N, int H, int W) {
+  if (N <= 0 || H <= 0 || W <= 0) return 0;
+  return carve(nullptr, precision, N, H, W).bytes;
+}
+
+int pfnl_reserve(pfnl_handle* h, int N, int H, int W) {
+  if (!h) {
+    set_error("pfnl_reserve: NULL handle");
+    return PFNL_ERR_BAD_ARG;
+  }
+  int rc = check_shape(N, H, W);
+  if (rc) return rc;
+  DeviceGuard guard(h->device);
+  return ensure_workspace(h, N, H, W);
+}
+
+int pfnl_set_graphs(pfnl_handle* h, int enable) {
+  if (!h) {
+    set_error("pfnl_set_graphs: NULL handle");
+    return PFNL_ERR_BAD_ARG;
+  }
+  h->graphs = enable != 0;
+  return PFNL_OK;
+}
+
+long long pfnl_launch_count(const pfnl_handle* h) { return h ? h->launches : 0; }
+
+int pfnl_profile(pfnl_handle* h, int enable) {
+  if (!h) {
+    set_error("pfnl_profile: NULL handle");
+    return PFNL_ERR_BAD_ARG;
+  }
+  h->prof.on = enable != 0;
+  return PFNL_OK;
+}
+
+int pfnl_profile_read(pfnl_handle* h, double* ms_by_kind, long long* launches_by_kind) {
+  if (!h || !ms_by_kind || !launches_by_kind) {
+    set_error("pfnl_profile_read: NULL argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  DeviceGuard guard(h->device);
+  PFNL_CUDA(cudaDeviceSynchronize());
+  for (int k = 0; k < kProfKinds; ++k) {
+    ms_by_kind[k] = 0.0;
+    launches_by_kind[k] = 0;
+  }
+  for (auto& r : h->prof.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      ms_by_kind[r.kind] += ms;
+      launches_by_kind[r.kind] += 1;
+    }
+    h->prof.pool.push_back(r.a);
+    h->prof.pool.push_back(r.b);
+  }
+  h->prof.recs.clear();
+  cudaGetLastError();
+  return PFNL_OK;
+}
+
+int pfnl_forward(pfnl_handle* h, const float* lr, int N, int H, int W, float* sr, void* stream) {
+  if (!h || !lr || !sr) {
+    set_error("pfnl_forward: NULL argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  int rc = check_shape(N, H, W);
+  if (rc) return rc;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  PFNL_CUDA(cudaStreamIsCapturing(s, &cap));
+  if (cap == cudaStreamCaptureStatusNone) {
+    if ((rc = ensure_workspace(h, N, H, W))) return rc;
+  } else if (carve(nullptr, h->precision, N, H, W).bytes > h->ws_cap) {
+    set_error("pfnl_forward: stream is capturing and the workspace for (%d,%d,%d) is not reserved", N, H, W);
+    return PFNL_ERR_BAD_ARG;
+  }
+  if (!h->graphs || h->prof.on || cap != cudaStreamCaptureStatusNone || s == nullptr)
+    return forward_launches(h, lr, N, H, W, sr, s);
+
+  auto key = std::make_tuple(N, H, W, (const void*)lr, (void*)sr);
+  auto it = h->graph_cache.find(key);
+  if (it == h->graph_cache.end()) {
+    cudaGraph_t graph = nullptr;
+    const long long before = h->launches;
+    PFNL_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    rc = forward_launches(h, lr, N, H, W, sr, s);
+    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    const long long nodes = h->launches - before;
+    h->launches = before;
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+    if (h->graph_cache.size() >= 16) {
+      for (auto& kv : h->graph_cache) cudaGraphExecDestroy(kv.second);
+      h->graph_cache.clear();
+      h->graph_nodes.clear();
+    }
+    it = h->graph_cache.emplace(key, exec).first;
+    h->graph_nodes[key] = nodes;
+  }
+  PFNL_CUDA(cudaGraphLaunch(it->second, s));
+  h->launches += h->graph_nodes[key];
+  return PFNL_OK;
+}
+
+int pfnl_forward_host(pfnl_handle* h, const float* lr_host, int N, int H, int W, float* sr_host, void* stream) {
+  if (!h || !lr_host || !sr_host) {
+    set_error("pfnl_forward_host: NULL argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  int rc = check_shape(N, H, W);
+  if (rc) return rc;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t in_bytes = (size_t)N * kFrames * H * W * 3 * sizeof(float);
+  const size_t out_bytes = (size_t)N * 16 * H * W * 3 * sizeof(float);
+  if (in_bytes > h->pin_in_cap) {
+    if (h->pin_in) cudaFreeHost(h->pin_in);
+    if (h->dev_in) cudaFree(h->dev_in);
+    h->pin_in = nullptr;
+    h->dev_in = nullptr;
+    h->pin_in_cap = 0;
+    PFNL_CUDA(cudaMallocHost((void**)&h->pin_in, in_bytes));
+    PFNL_CUDA(cudaMalloc((void**)&h->dev_in, in_bytes));
+    h->pin_in_cap = in_bytes;
+  }
+  if (out_bytes > h->pin_out_cap) {
+    if (h->pin_out) cudaFreeHost(h->pin_out);
+    if (h->dev_out) cudaFree(h->dev_out);
+    h->pin_out = nullptr;
+    h->dev_out = nullptr;
+    h->pin_out_cap = 0;
+    PFNL_CUDA(cudaMallocHost((void**)&h->pin_out, out_bytes));
+    PFNL_CUDA(cudaMalloc((void**)&h->dev_out, out_bytes));
+    h->pin_out_cap = out_bytes;
+  }
+  // A registered (pinned) caller buffer is copied directly; pageable memory goes through staging.
+  cudaPointerAttributes at;
+  const bool in_pinned = cudaPointerGetAttributes(&at, lr_host) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  const bool out_pinned = cudaPointerGetAttributes(&at, sr_host) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  const float* src = lr_host;
+  if (!in_pinned) {
+    memcpy(h->pin_in, lr_host, in_bytes);
+    src = h->pin_in;
+  }
+  PFNL_CUDA(cudaMemcpyAsync(h->dev_in, src, in_bytes, cudaMemcpyHostToDevice, s));
+  if ((rc = pfnl_forward(h, h->dev_in, N, H, W, h->dev_out, stream))) return rc;
+  float* dst = out_pinned ? sr_host : h->pin_out;
+  PFNL_CUDA(cudaMemcpyAsync(dst, h->dev_out, out_bytes, cudaMemcpyDeviceToHost, s));
+  PFNL_CUDA(cudaStreamSynchronize(s));
+  if (!out_pinned) memcpy(sr_host, h->pin_out, out_bytes);
+  return PFNL_OK;
+}
+
+int pfnl_mse(pfnl_handle* h, const float* sr, const float* hr, int N, int H4, int W4, float* mse, void* stream) {
+  if (!h || !sr || !hr || !mse) {
+    set_error("pfnl_mse: NULL argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  if (N <= 0 || H4 <= 0 || W4 <= 0) {
+    set_error("pfnl_mse: bad shape N=%d H4=%d W4=%d", N, H4, W4);
+    return PFNL_ERR_BAD_SHAPE;
+  }
+  DeviceGuard guard(h->device);
+  if (N > h->mse_cap) {
+    if (h->mse_partial) {
+      PFNL_CUDA(cudaDeviceSynchronize());
+      PFNL_CUDA(cudaFree(h->mse_partial));
+      h->mse_partial = nullptr;
+      h->mse_cap = 0;
+    }
+    PFNL_CUDA(cudaMalloc((void**)&h->mse_partial, (size_t)N * kMseChunks * sizeof(double)));
+    h->mse_cap = N;
+  }
+  int rc = launch_mse(sr, hr, N, (long long)H4 * W4 * 3, h->mse_partial, mse, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->launches += 2;
+  return PFNL_OK;
+}
+
+int pfnl_pack_tokens(pfnl_handle* h, const float* lr, int N, int H, int W, float* tokens, void* stream) {
+  if (!h || !lr || !tokens) {
+    set_error("pfnl_pack_tokens: NULL argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  int rc = check_shape(N, H, W);
+  if (rc) return rc;
+  DeviceGuard guard(h->device);
+  if ((rc = launch_pack_tokens(lr, N, H, W, tokens, (cudaStream_t)stream))) return rc;
+  h->launches += 1;
+  return PFNL_OK;
+}
+
+int pfnl_nonlocal(pfnl_handle* h, const float* tokens, int N, int L, float* out, void* stream) {
+  if (!h || !tokens || !out) {
+    set_error("pfnl_nonlocal: NULL argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  if (N <= 0 || L <= 0) {
+    set_error("pfnl_nonlocal: bad shape N=%d L=%d", N, L);
+    return PFNL_ERR_BAD_SHAPE;
+  }
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->precision == PFNL_PREC_TC_FP16) return tc_nonlocal_tokens(h->tcw, tokens, N, L, out, s, &h->launches);
+  // scratch: G and Y live in the workspace sized for an equivalent (N, 2, 2L) frame
+  int rc = ensure_workspace(h, N, 2, 2 * L);
+  if (rc) return rc;
+  Workspace w = carve(h->ws, h->precision, N, 2, 2 * L);
+  if ((rc = launch_nl_linear(tokens, N * L, h->nl_g_w, h->nl_g_b, w.g, s))) return rc;
+  if ((rc = launch_nl_flash_ffma(tokens, w.g, N, L, w.yatt, s))) return rc;
+  if ((rc = launch_nl_linear(w.yatt, N * L, h->nl_w_w, h->nl_w_b, out, s))) return rc;
+  h->launches += 3;
+  return PFNL_OK;
+}
+
+int pfnl_depth_to_space(pfnl_handle* h, const float* in, int N, int H, int W, int C, int block, float* out,
+                        void* stream) {
+  if (!h || !in || !out) {
+    set_error("pfnl_depth_to_space: NULL argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || block <= 0 || C % (block * block) != 0) {
+    set_error("pfnl_depth_to_space: bad shape N=%d H=%d W=%d C=%d block=%d", N, H, W, C, block);
+    return PFNL_ERR_BAD_SHAPE;
+  }
+  DeviceGuard guard(h->device);
+  int rc = launch_depth_to_space(in, N, H, W, C, block, out, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->launches += 1;
+  return PFNL_OK;
+}
+
+int pfnl_space_to_depth(pfnl_handle* h, const float* in, int N, int H, int W, int C, int block, float* out,
+                        void* stream) {
+  if (!h || !in || !out) {
+    set_error("pfnl_space_to_depth: NULL argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || block <= 0 || H % block != 0 || W % block != 0) {
+    set_error("pfnl_space_to_depth: bad shape N=%d H=%d W=%d C=%d block=%d", N, H, W, C, block);
+    return PFNL_ERR_BAD_SHAPE;
+  }
+  DeviceGuard guard(h->device);
+  int rc = launch_space_to_depth(in, N, H, W, C, block, out, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->launches += 1;
+  return PFNL_OK;
+}
+
+int pfnl_conv2d_nhwc(pfnl_handle* h, const float* in, int N, int H, int W, int Cin, const float* kernel,
+                     const float* bias, int k, int Cout, int act, const float* residual, float* out, void* stream) {
+  if (!h || !in || !kernel || !bias || !out) {
+    set_error("pfnl_conv2d_nhwc: NULL argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (k != 1 && k != 3 && k != 5)) {
+    set_error("pfnl_conv2d_nhwc: bad shape N=%d H=%d W=%d Cin=%d Cout=%d k=%d", N, H, W, Cin, Cout, k);
+    return PFNL_ERR_BAD_SHAPE;
+  }
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool aligned =
+      ((((uintptr_t)in) | ((uintptr_t)out) | ((uintptr_t)bias) | ((uintptr_t)residual)) & 15) == 0;
+  int rc;
+  if ((k == 1 || k == 3) && Cin % 16 == 0 && Cout % 4 == 0 && Cout <= 64 && aligned) {
+    const size_t need = conv_ffma_packed_floats(k, Cin) * sizeof(float);
+    if (need > h->pack_cap) {
+      if (h->pack_scratch) {
+        PFNL_CUDA(cudaDeviceSynchronize());
+        PFNL_CUDA(cudaFree(h->pack_scratch));
+        h->pack_scratch = nullptr;
+        h->pack_cap = 0;
+      }
+      PFNL_CUDA(cudaMalloc((void**)&h->pack_scratch, need));
+      h->pack_cap = need;
+    }
+    if ((rc = launch_pack_conv_ffma_weights(kernel, k, Cin, Cout, h->pack_scratch, s))) return rc;
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nslices = 1;
+    a.slice_ch = Cin;
+    a.slice[0] = make_slice(in, (long long)H * W * Cin, 1, Cin);
+    a.images = N;
+    a.H = H;
+    a.W = W;
+    a.wpack = h->pack_scratch;
+    a.bias = bias;
+    a.cout = Cout;
+    a.act = act;
+    a.residual = residual;
+    a.out = out;
+    if ((rc = launch_conv_ffma(k, a, s))) return rc;
+    h->launches += 2;
+  } else {
+    if ((rc = launch_conv_direct(in, N, H, W, Cin, kernel, bias, k, Cout, act, residual, out, s))) return rc;
+    h->launches += 1;
+  }
+  return PFNL_OK;
+}
+
+int pfnl_bicubic4(pfnl_handle* h, const float* in, int N, int H, int W, int C, float* out, void* stream) {
+  if (!h || !in || !out) {
+    set_error("pfnl_bicubic4: NULL argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0) {
+    set_error("pfnl_bicubic4: bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
+    return PFNL_ERR_BAD_SHAPE;
+  }
+  DeviceGuard guard(h->device);
+  int rc = launch_bicubic4(in, N, H, W, C, out, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->launches += 1;
+  return PFNL_OK;
+}
+
+int pfnl_pfrb(pfnl_handle* h, int blk, const float* frames, int N, int H, int W, float* frames_out, void* stream) {
+  if (!h || !frames || !frames_out) {
+    set_error("pfnl_pfrb: NULL argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  if (blk < 0 || blk >= PFNL_NUM_BLOCK) {
+    set_error("pfnl_pfrb: block index %d out of range", blk);
+    return PFNL_ERR_BAD_ARG;
+  }
+  int rc = check_shape(N, H, W);
+  if (rc) return rc;
+  DeviceGuard guard(h->device);
+  if ((rc = ensure_workspace(h, N, H, W))) return rc;
+  Workspace w = carve(h->ws, h->precision, N, H, W);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->precision == PFNL_PREC_FP32) return pfrb_fp32(h, blk, frames, frames_out, w, N, H, W, s);
+  return tc_pfrb_fp32io(h->tcw, w.tc, h->precision, blk, frames, N, H, W, frames_out, s, &h->launches);
+}
+
+}  // extern "C"

@@ -1,0 +1,401 @@
+// fp32 (FFMA) convolution kernels: the <=1e-3 parity path (PFNL_PREC_FP32) and the shape-
+// generic fallbacks behind pfnl_conv2d_nhwc.  All follow tf.layers.Conv2D(strides=1,
+// padding='same') on NHWC with HWIO kernels (model/pfnl.py:48-53): cross-correlation, zero pad
+// (k-1)/2, + bias, optional leaky_relu(0.2), optional residual add (model/pfnl.py:71).
+//
+//   conv_ffma_kernel<KS>  implicit GEMM, tile = 8x16 output pixels x 64 couts per 256-thread CTA,
+//                         K streamed in 16-channel chunks (cp.async double buffer; halo patch +
+//                         that chunk's KS*KS*16x64 weights in smem); each thread owns 8 pixels x
+//                         4 couts.  Channel concats (pfnl.py:67,69,73) are read as K-slices.
+//   conv0_kernel          5x5, 3->64, shared over the 7 frames (pfnl.py:48,61-62).
+//   tail_kernel           depth_to_space -> convmerge2 -> depth_to_space -> + bicubic skip
+//                         (pfnl.py:76-80) in one pass.
+//   conv_direct_kernel    any shape, one thread per output element.
+#include "bicubic.cuh"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pfnl {
+
+template <int KS>
+struct FfmaCfg {
+  static constexpr int TH = 8, TW = 16;
+  static constexpr int PH = TH + KS - 1;
+  static constexpr int PWV = TW + KS - 1;             // valid patch width (pixels)
+  static constexpr int PITCH = (KS == 1) ? 17 : PWV;  // smem row pitch (pixels); keeps the two
+                                                      // pixel groups of a warp on different banks
+  static constexpr int PIXF = 20;                     // floats per smem pixel (16 + 4 pad)
+  static constexpr int PATCH_FLOATS = PH * PITCH * PIXF;
+  static constexpr int W_FLOATS = KS * KS * 16 * 64;
+  static constexpr int STAGE_FLOATS = PATCH_FLOATS + W_FLOATS;
+  static constexpr int SMEM_BYTES = 2 * STAGE_FLOATS * 4;
+};
+
+template <int KS>
+__global__ void __launch_bounds__(256, 2) conv_ffma_kernel(const ConvArgs a) {
+  using C = FfmaCfg<KS>;
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_x = ceil_div(a.W, C::TW);
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x % tiles_x;
+  const int img = blockIdx.y;
+  const int y0 = ty * C::TH, x0 = tx * C::TW;
+  const int cg = lane & 15;              // cout group: couts cg*4..cg*4+3
+  const int r = 2 * (warp & 3) + (lane >> 4);  // tile row of this thread's 8-pixel run
+  const int hx = warp >> 2;              // which 8-wide half of the 16-wide tile
+  const int cps = a.slice_ch >> 4;       // 16-channel chunks per slice
+  const int nchunks = a.nslices * cps;
+  constexpr int PAD = (KS - 1) / 2;
+
+  auto stage = [&](int q, int buf) {
+    float* patch = smem + buf * C::STAGE_FLOATS;
+    float* wsm = patch + C::PATCH_FLOATS;
+    const int sidx = q / cps;
+    const int c0 = (q - sidx * cps) << 4;
+    const ConvSlice sl = a.slice[sidx];
+    const float* base = sl.ptr + (long long)(img / sl.img_div) * sl.img_stride + c0;
+    for (int i = tid; i < C::PH * C::PWV * 4; i += 256) {
+      const int part = i & 3, p = i >> 2;
+      const int py = p / C::PWV, px = p - py * C::PWV;
+      const int gy = y0 + py - PAD, gx = x0 + px - PAD;
+      const bool ok = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+      const float* src = ok ? base + ((long long)gy * a.W + gx) * sl.pix_stride + part * 4 : sl.ptr;
+      cp_async16(patch + (py * C::PITCH + px) * C::PIXF + part * 4, src, ok ? 16 : 0);
+    }
+    const float* wsrc = a.wpack + (long long)q * C::W_FLOATS;
+    for (int i = tid; i < C::W_FLOATS / 4; i += 256) cp_async16(wsm + i * 4, wsrc + i * 4, 16);
+  };
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  stage(0, 0);
+  cp_async_commit();
+  for (int q = 0; q < nchunks; ++q) {
+    const int buf = q & 1;
+    if (q + 1 < nchunks) {
+      stage(q + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* patch = smem + buf * C::STAGE_FLOATS;
+    const float* wsm = patch + C::PATCH_FLOATS;
+#pragma unroll 1
+    for (int tap = 0; tap < KS * KS; ++tap) {
+      const int dy = tap / KS, dx = tap - dy * KS;
+      const float* arow = patch + ((r + dy) * C::PITCH + hx * 8 + dx) * C::PIXF;
+      const float* wt = wsm + tap * 16 * 64 + cg * 4;
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const float4 b0 = *reinterpret_cast<const float4*>(wt + (k4 * 4 + 0) * 64);
+        const float4 b1 = *reinterpret_cast<const float4*>(wt + (k4 * 4 + 1) * 64);
+        const float4 b2 = *reinterpret_cast<const float4*>(wt + (k4 * 4 + 2) * 64);
+        const float4 b3 = *reinterpret_cast<const float4*>(wt + (k4 * 4 + 3) * 64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 av = *reinterpret_cast<const float4*>(arow + i * C::PIXF + k4 * 4);
+          acc[i][0] = fmaf(av.x, b0.x, acc[i][0]);
+          acc[i][1] = fmaf(av.x, b0.y, acc[i][1]);
+          acc[i][2] = fmaf(av.x, b0.z, acc[i][2]);
+          acc[i][3] = fmaf(av.x, b0.w, acc[i][3]);
+          acc[i][0] = fmaf(av.y, b1.x, acc[i][0]);
+          acc[i][1] = fmaf(av.y, b1.y, acc[i][1]);
+          acc[i][2] = fmaf(av.y, b1.z, acc[i][2]);
+          acc[i][3] = fmaf(av.y, b1.w, acc[i][3]);
+          acc[i][0] = fmaf(av.z, b2.x, acc[i][0]);
+          acc[i][1] = fmaf(av.z, b2.y, acc[i][1]);
+          acc[i][2] = fmaf(av.z, b2.z, acc[i][2]);
+          acc[i][3] = fmaf(av.z, b2.w, acc[i][3]);
+          acc[i][0] = fmaf(av.w, b3.x, acc[i][0]);
+          acc[i][1] = fmaf(av.w, b3.y, acc[i][1]);
+          acc[i][2] = fmaf(av.w, b3.z, acc[i][2]);
+          acc[i][3] = fmaf(av.w, b3.w, acc[i][3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  const int co = cg * 4;
+  const int gy = y0 + r;
+  if (co < a.cout && gy < a.H) {
+    const float4 bs = *reinterpret_cast<const float4*>(a.bias + co);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int gx = x0 + hx * 8 + i;
+      if (gx < a.W) {
+        const long long o = (((long long)img * a.H + gy) * a.W + gx) * a.cout + co;
+        float4 v = make_float4(acc[i][0] + bs.x, acc[i][1] + bs.y, acc[i][2] + bs.z, acc[i][3] + bs.w);
+        if (a.act) {
+          v.x = lrelu(v.x);
+          v.y = lrelu(v.y);
+          v.z = lrelu(v.z);
+          v.w = lrelu(v.w);
+        }
+        if (a.residual) {
+          const float4 rs = *reinterpret_cast<const float4*>(a.residual + o);
+          v.x += rs.x;
+          v.y += rs.y;
+          v.z += rs.z;
+          v.w += rs.w;
+        }
+        *reinterpret_cast<float4*>(a.out + o) = v;
+      }
+    }
+  }
+}
+
+size_t conv_ffma_packed_floats(int ks, int cin) { return (size_t)(cin / 16) * ks * ks * 16 * 64; }
+
+// HWIO [ks,ks,cin,cout] -> [cin/16][ks*ks][16][64] with cout zero-padded to 64 (device side).
+__global__ void pack_conv_ffma_weights_kernel(const float* __restrict__ hwio, int taps, int cin, int cout,
+                                              float* __restrict__ packed) {
+  const long long total = (long long)(cin / 16) * taps * 16 * 64;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(e & 63);
+    const int k = (int)((e >> 6) & 15);
+    const long long r = e >> 10;
+    const int tap = (int)(r % taps);
+    const int q = (int)(r / taps);
+    packed[e] = co < cout ? hwio[((long long)tap * cin + q * 16 + k) * cout + co] : 0.f;
+  }
+}
+
+int launch_pack_conv_ffma_weights(const float* hwio_dev, int ks, int cin, int cout, float* packed_dev,
+                                  cudaStream_t s) {
+  const long long total = (long long)conv_ffma_packed_floats(ks, cin);
+  if (total == 0) return PFNL_OK;
+  long long bl = (total + 255) / 256;
+  if (bl > 1024) bl = 1024;
+  pack_conv_ffma_weights_kernel<<<(int)bl, 256, 0, s>>>(hwio_dev, ks * ks, cin, cout, packed_dev);
+  PFNL_LAUNCH_CHECK();
+  return PFNL_OK;
+}
+
+// Per-device one-time setup (opt-in to >48 KB dynamic shared memory); called by pfnl_create.
+int init_conv_ffma() {
+  PFNL_CUDA(cudaFuncSetAttribute(conv_ffma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 FfmaCfg<3>::SMEM_BYTES));
+  PFNL_CUDA(cudaFuncSetAttribute(conv_ffma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 FfmaCfg<1>::SMEM_BYTES));
+  return PFNL_OK;
+}
+
+int launch_conv_ffma(int ks, const ConvArgs& a, cudaStream_t s) {
+  if (a.images <= 0 || a.H <= 0 || a.W <= 0) return PFNL_OK;
+  if (a.slice_ch % 16 != 0 || a.cout % 4 != 0 || a.cout > 64 || a.nslices < 1 || a.nslices > 7) {
+    set_error("launch_conv_ffma: unsupported shape (slice_ch=%d cout=%d nslices=%d)", a.slice_ch, a.cout, a.nslices);
+    return PFNL_ERR_BAD_SHAPE;
+  }
+  dim3 grid(ceil_div(a.W, 16) * ceil_div(a.H, 8), a.images);
+  if (ks == 3) {
+    conv_ffma_kernel<3><<<grid, 256, FfmaCfg<3>::SMEM_BYTES, s>>>(a);
+  } else if (ks == 1) {
+    conv_ffma_kernel<1><<<grid, 256, FfmaCfg<1>::SMEM_BYTES, s>>>(a);
+  } else {
+    set_error("launch_conv_ffma: ks=%d unsupported", ks);
+    return PFNL_ERR_BAD_ARG;
+  }
+  PFNL_LAUNCH_CHECK();
+  return PFNL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Generic direct conv: one thread per output element.  Correctness fallback for shapes the
+// tiled kernel does not cover (Cin % 16 != 0, Cout > 64, k = 5).
+// ---------------------------------------------------------------------------------------
+__global__ void conv_direct_kernel(const float* __restrict__ in, int N, int H, int W, int Cin,
+                                   const float* __restrict__ kernel, const float* __restrict__ bias, int k, int Cout,
+                                   int act, const float* __restrict__ residual, float* __restrict__ out) {
+  const long long total = (long long)N * H * W * Cout;
+  const int pad = (k - 1) / 2;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    int co = (int)(e % Cout);
+    long long r = e / Cout;
+    int x = (int)(r % W);
+    r /= W;
+    int y = (int)(r % H);
+    int n = (int)(r / H);
+    float acc = 0.f;
+    for (int i = 0; i < k; ++i) {
+      int yy = y + i - pad;
+      if (yy < 0 || yy >= H) continue;
+      for (int j = 0; j < k; ++j) {
+        int xx = x + j - pad;
+        if (xx < 0 || xx >= W) continue;
+        const float* ip = in + (((long long)n * H + yy) * W + xx) * Cin;
+        const float* kp = kernel + ((long long)(i * k + j) * Cin) * Cout + co;
+        for (int c = 0; c < Cin; ++c) acc = fmaf(ip[c], kp[(long long)c * Cout], acc);
+      }
+    }
+    float v = acc + bias[co];
+    if (act) v = lrelu(v);
+    if (residual) v += residual[e];
+    out[e] = v;
+  }
+}
+
+int launch_conv_direct(const float* in, int N, int H, int W, int Cin, const float* kernel, const float* bias, int k,
+                       int Cout, int act, const float* residual, float* out, cudaStream_t s) {
+  long long total = (long long)N * H * W * Cout;
+  if (total == 0) return PFNL_OK;
+  int threads = 256;
+  long long bl = (total + threads - 1) / threads;
+  if (bl > 148LL * 32) bl = 148LL * 32;
+  conv_direct_kernel<<<(int)bl, threads, 0, s>>>(in, N, H, W, Cin, kernel, bias, k, Cout, act, residual, out);
+  PFNL_LAUNCH_CHECK();
+  return PFNL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// conv0: 5x5, 3 -> 64, leaky_relu, one layer shared by the 7 frames (model/pfnl.py:48,61-62).
+// Reads frame t as channels 3t..3t+2 of inp21 [N,H,W,21] (the tf.split of pfnl.py:61).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ inp21, int H, int W,
+                                                    const float* __restrict__ w, const float* __restrict__ bias,
+                                                    float* __restrict__ out) {
+  __shared__ __align__(16) float wsm[75 * 64];
+  __shared__ float patch[20 * 20 * 3];
+  const int tid = threadIdx.x;
+  const int tiles_x = ceil_div(W, 16);
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x % tiles_x;
+  const int img = blockIdx.y;  // n*7 + t
+  const int n = img / kFrames, t = img % kFrames;
+  const int y0 = ty * 16, x0 = tx * 16;
+  for (int i = tid; i < 75 * 64; i += 256) wsm[i] = w[i];
+  for (int i = tid; i < 20 * 20 * 3; i += 256) {
+    int c = i % 3, p = i / 3;
+    int py = p / 20, px = p % 20;
+    int gy = y0 + py - 2, gx = x0 + px - 2;
+    float v = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = inp21[(((long long)n * H + gy) * W + gx) * 21 + t * 3 + c];
+    patch[i] = v;
+  }
+  __syncthreads();
+  const int py = tid >> 4, px = tid & 15;
+  float acc[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+#pragma unroll 1
+  for (int dy = 0; dy < 5; ++dy) {
+#pragma unroll
+    for (int dx = 0; dx < 5; ++dx) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float av = patch[((py + dy) * 20 + px + dx) * 3 + c];
+        const float4* wr = reinterpret_cast<const float4*>(wsm + ((dy * 5 + dx) * 3 + c) * 64);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 b = wr[j];
+          acc[4 * j + 0] = fmaf(av, b.x, acc[4 * j + 0]);
+          acc[4 * j + 1] = fmaf(av, b.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(av, b.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(av, b.w, acc[4 * j + 3]);
+        }
+      }
+    }
+  }
+  const int gy = y0 + py, gx = x0 + px;
+  if (gy < H && gx < W) {
+    float4* o = reinterpret_cast<float4*>(out + (((long long)img * H + gy) * W + gx) * 64);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 bs = *reinterpret_cast<const float4*>(bias + 4 * j);
+      o[j] = make_float4(lrelu(acc[4 * j] + bs.x), lrelu(acc[4 * j + 1] + bs.y), lrelu(acc[4 * j + 2] + bs.z),
+                         lrelu(acc[4 * j + 3] + bs.w));
+    }
+  }
+}
+
+int launch_conv0(const float* inp21, int N, int H, int W, const float* w_hwio, const float* bias, float* out,
+                 cudaStream_t s) {
+  if (N <= 0) return PFNL_OK;
+  dim3 grid(ceil_div(W, 16) * ceil_div(H, 16), N * kFrames);
+  conv0_kernel<<<grid, 256, 0, s>>>(inp21, H, W, w_hwio, bias, out);
+  PFNL_LAUNCH_CHECK();
+  return PFNL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Upscaler tail (model/pfnl.py:76-80):
+//   large1 = depth_to_space(merge,2); out1 = convmerge2(large1) (3x3, 12->12, no activation);
+//   out = depth_to_space(out1,2); return out + bicubic(x[:,3]).
+// One thread per out1 pixel (2H x 2W): reads large1 through the DCR index map (12 contiguous
+// floats of merge per tap), then writes its 2x2 HR pixels with the bicubic skip added.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) tail_kernel(const float* __restrict__ merge, const float* __restrict__ lr,
+                                                   int N, int H, int W, const float* __restrict__ w2,
+                                                   const float* __restrict__ b2, float* __restrict__ sr) {
+  __shared__ float wsm[9 * 12 * 12];
+  __shared__ float bsm[12];
+  for (int i = threadIdx.x; i < 9 * 12 * 12; i += blockDim.x) wsm[i] = w2[i];
+  if (threadIdx.x < 12) bsm[threadIdx.x] = b2[threadIdx.x];
+  __syncthreads();
+  const int H2 = 2 * H, W2 = 2 * W;
+  const long long total = (long long)N * H2 * W2;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(e % W2);
+    long long r = e / W2;
+    const int y = (int)(r % H2);
+    const int n = (int)(r / H2);
+    float acc[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = y + dy - 1;
+      if (yy < 0 || yy >= H2) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xx = x + dx - 1;
+        if (xx < 0 || xx >= W2) continue;
+        const float4* src = reinterpret_cast<const float4*>(
+            merge + (((long long)n * H + (yy >> 1)) * W + (xx >> 1)) * 48 + (((yy & 1) << 1) + (xx & 1)) * 12);
+        const float4 v0 = src[0], v1 = src[1], v2 = src[2];
+        const float v[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+        const float* wt = wsm + (dy * 3 + dx) * 144;
+#pragma unroll
+        for (int ci = 0; ci < 12; ++ci)
+#pragma unroll
+          for (int co = 0; co < 12; ++co) acc[co] = fmaf(v[ci], wt[ci * 12 + co], acc[co]);
+      }
+    }
+    const float* centre = lr + ((long long)n * kFrames + kFrames / 2) * H * W * 3;
+    const int H4 = 4 * H, W4 = 4 * W;
+#pragma unroll
+    for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+      for (int ox = 0; ox < 2; ++ox) {
+        const int Y = 2 * y + oy, X = 2 * x + ox;
+        float* o = sr + (((long long)n * H4 + Y) * W4 + X) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float outv = acc[(oy * 2 + ox) * 3 + c] + bsm[(oy * 2 + ox) * 3 + c];
+          o[c] = outv + bicubic4_at(centre, H, W, 3, Y, X, c);
+        }
+      }
+  }
+}
+
+int launch_tail(const float* merge, const float* lr, int N, int H, int W, const float* w2_hwio, const float* b2,
+                float* sr, cudaStream_t s) {
+  long long total = (long long)N * 2 * H * 2 * W;
+  if (total == 0) return PFNL_OK;
+  int threads = 128;
+  long long bl = (total + threads - 1) / threads;
+  if (bl > 148LL * 32) bl = 148LL * 32;
+  tail_kernel<<<(int)bl, threads, 0, s>>>(merge, lr, N, H, W, w2_hwio, b2, sr);
+  PFNL_LAUNCH_CHECK();
+  return PFNL_OK;
+}
+
+}  // namespace pfnl

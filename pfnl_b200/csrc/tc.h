@@ -1,0 +1,73 @@
+// Interface of the tensor-core (tcgen05 / TMA) path: conv_tc.cu, nonlocal_tc.cu, tc_host.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include <functional>
+#include <vector>
+
+#include "../../include/pfnl_b200.h"
+#include "kernels.h"
+
+namespace pfnl {
+
+struct TcRawWeights {  // fp32 HWIO device pointers owned by the handle
+  const float *nl_g_w, *nl_g_b, *nl_w_w, *nl_w_b;
+  const float *conv0_w, *conv0_b;
+  const float* conv1_w[PFNL_NUM_BLOCK];
+  const float* conv1_b[PFNL_NUM_BLOCK];
+  const float* conv10_w[PFNL_NUM_BLOCK];
+  const float* conv10_b[PFNL_NUM_BLOCK];
+  const float* conv2_w[PFNL_NUM_BLOCK];
+  const float* conv2_b[PFNL_NUM_BLOCK];
+  const float *merge1_w, *merge1_b;
+};
+
+struct TcWeights {
+  int precision = 0;
+  int nsplit = 1;  // 1: fp16, 2: hi/lo fp16 planes
+  TcRawWeights raw{};
+  // UMMA-ready fp16 weight images (K-major, 128B swizzle), one per layer:
+  //   conv1_i  [nsplit][9 taps][64 co][64 ci]
+  //   conv10_i [nsplit][7 slices][64 co][64 ci]
+  //   conv2b_i [nsplit][9][64][64]   (base half of conv2, Cin 0-63)
+  //   conv2f_i [nsplit][9][64][64]   (frame half of conv2, Cin 64-127)
+  //   merge1   [nsplit][7*9][64 co (48 real)][64 ci]
+  void* conv1[PFNL_NUM_BLOCK] = {};
+  void* conv10[PFNL_NUM_BLOCK] = {};
+  void* conv2b[PFNL_NUM_BLOCK] = {};
+  void* conv2f[PFNL_NUM_BLOCK] = {};
+  void* merge1 = nullptr;
+  float* zero_bias = nullptr;  // [64] zeros
+  // non-local (precision 2): fp16 Wg^T image etc.
+  void* nl_priv = nullptr;
+};
+
+struct TcWorkspace {
+  // activations as fp16 NHWC planes [images,H,W,64]; plane 0 = hi, plane 1 = lo (x3 mode)
+  void* actA[2];   // inp0 (residual stream)
+  void* actB[2];   // inp1
+  void* base[2];   // conv10 output [N,H,W,64]
+  float* pbase;    // fp32 partial conv2 over the base half [N,H,W,64]
+  void* nl_x16;    // fp16 token matrix [N*L,96]
+  void* nl_priv;
+};
+
+void tc_carve(TcWorkspace& w, int precision, int N, int H, int W, const std::function<char*(size_t)>& take);
+int tc_init(TcWeights& tw, int precision, const TcRawWeights& raw, std::vector<void*>& allocs);
+void tc_destroy(TcWeights& tw);
+
+// conv0 .. convmerge1 (model/pfnl.py:61-74): inp21 [N,H,W,21] fp32 -> merge [N,H,W,48] fp32
+int tc_trunk(const TcWeights& tw, TcWorkspace& w, int precision, const float* inp21, int N, int H, int W,
+             float* merge, cudaStream_t s, long long* launches, Profiler* prof);
+// tokens [N,L,84] (+ lr for the residual) -> inp21 [N,H,W,21]   (model/pfnl.py:58-60)
+int tc_nonlocal(const TcWeights& tw, TcWorkspace& w, const float* tokens, const float* lr, int N, int H, int W,
+                float* inp21, cudaStream_t s, long long* launches, Profiler* prof);
+// tokens [N,L,84] -> NonLocalBlock output [N,L,84]
+int tc_nonlocal_tokens(const TcWeights& tw, const float* tokens, int N, int L, float* out, cudaStream_t s,
+                       long long* launches);
+// One PFRB with fp32 frames in/out (conversion kernels around the tensor-core block).
+int tc_pfrb_fp32io(const TcWeights& tw, TcWorkspace& w, int precision, int blk, const float* frames, int N, int H,
+                   int W, float* frames_out, cudaStream_t s, long long* launches);
+
+}  // namespace pfnl

@@ -1,0 +1,385 @@
+"""Drop-in host side of the PFNL forward path: same class/method names, argument meaning,
+directory conventions and tensor layout as the reference's model/pfnl.py, with every
+tensor op executed by libpfnl_b200.so on a B200 (PyTorch tensors are only the buffer
+currency: device memory, streams, pinned host memory).
+
+    reference                                   here
+    PFNL.forward(x)               pfnl.py:39    PFNL.forward(x)        x [N,7,H,W,3] -> [N,1,4H,4W,3]
+    sess.run(SR_test, feed_dict)  pfnl.py:252   PFNL.forward(numpy)    host in -> host out
+    eval_mse                      pfnl.py:90    PFNL.eval_mse(sr, hr)  -> [N,1]
+    test_video_truth              pfnl.py:203   same signature
+    test_video_lr                 pfnl.py:264   same signature (alias: testvideo, README.md:31)
+    testvideos                    pfnl.py:322   same signature
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import os
+import time
+from os.path import join
+
+import numpy as np
+import torch
+
+from . import _lib, weights as _weights
+from ._lib import check, lib
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Engine:
+    """One libpfnl_b200 handle (one device).  Thin, typed wrapper over the C ABI."""
+
+    def __init__(self, weights, device=0, precision="fp32", graphs=True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("pfnl_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self.precision = precision
+        prec = _lib.PRECISIONS[precision]
+        st, keep = _weights.to_struct(weights)
+        h = C.c_void_p()
+        check(lib.pfnl_create(C.byref(h), self.device.index, C.byref(st), prec))
+        del keep
+        self._h = h
+        check(lib.pfnl_set_graphs(self._h, 1 if graphs else 0))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.pfnl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers -------------------------------------------------------------------------
+    def _chk_in(self, t, ndim=None):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError("expected a contiguous float32 CUDA tensor")
+        if t.device != self.device:
+            raise ValueError(f"tensor on {t.device}, engine on {self.device}")
+        if ndim is not None and t.dim() != ndim:
+            raise ValueError(f"expected {ndim} dims, got {tuple(t.shape)}")
+
+    @property
+    def launches(self):
+        return int(lib.pfnl_launch_count(self._h))
+
+    PROF_KINDS = ("pack_tokens", "nonlocal", "conv0", "conv1_3x3", "conv10_1x1", "conv2_3x3", "convmerge1",
+                  "tail", "other")
+
+    def profile(self, enable):
+        """Bracket every launch class with CUDA events (bypasses CUDA graphs while on)."""
+        check(lib.pfnl_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """-> {class: (total_ms, launches)} since the last read (synchronises the device)."""
+        ms = (C.c_double * len(self.PROF_KINDS))()
+        cnt = (C.c_longlong * len(self.PROF_KINDS))()
+        check(lib.pfnl_profile_read(self._h, ms, cnt))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROF_KINDS)}
+
+    def reserve(self, n, h, w):
+        check(lib.pfnl_reserve(self._h, n, h, w))
+
+    def workspace_bytes(self, n, h, w):
+        return int(lib.pfnl_workspace_bytes(_lib.PRECISIONS[self.precision], n, h, w))
+
+    # -- whole forward -------------------------------------------------------------------
+    def forward(self, x, out=None):
+        self._chk_in(x, 5)
+        n, f, h, w, c = x.shape
+        if f != _lib.NUM_FRAMES or c != 3:
+            raise ValueError(f"input must be [N,7,H,W,3], got {tuple(x.shape)}")
+        if out is None:
+            out = torch.empty((n, 1, h * 4, w * 4, 3), dtype=torch.float32, device=self.device)
+        check(lib.pfnl_forward(self._h, _ptr(x), n, h, w, _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def forward_host(self, x, out=None):
+        """numpy / CPU-tensor in, numpy out (H2D + forward + D2H inside the call)."""
+        xt = torch.as_tensor(x, dtype=torch.float32).contiguous()
+        n, f, h, w, c = xt.shape
+        if f != _lib.NUM_FRAMES or c != 3:
+            raise ValueError(f"input must be [N,7,H,W,3], got {tuple(xt.shape)}")
+        if out is None:
+            out = torch.empty((n, 1, h * 4, w * 4, 3), dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(lib.pfnl_forward_host(self._h, C.c_void_p(xt.data_ptr()), n, h, w, C.c_void_p(out.data_ptr()),
+                                        _stream_ptr(self.device)))
+        return out
+
+    def mse(self, sr, hr):
+        self._chk_in(sr, 5)
+        self._chk_in(hr, 5)
+        n, _, h4, w4, _ = sr.shape
+        out = torch.empty((n,), dtype=torch.float32, device=self.device)
+        check(lib.pfnl_mse(self._h, _ptr(sr), _ptr(hr), n, h4, w4, _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    # -- stage-level ---------------------------------------------------------------------
+    def pack_tokens(self, x):
+        self._chk_in(x, 5)
+        n, _, h, w, _ = x.shape
+        out = torch.empty((n, (h // 2) * (w // 2), _lib.NL_CH), dtype=torch.float32, device=self.device)
+        check(lib.pfnl_pack_tokens(self._h, _ptr(x), n, h, w, _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def nonlocal_block(self, tokens):
+        self._chk_in(tokens, 3)
+        n, l, c = tokens.shape
+        if c != _lib.NL_CH:
+            raise ValueError("tokens must be [N,L,84]")
+        out = torch.empty_like(tokens)
+        check(lib.pfnl_nonlocal(self._h, _ptr(tokens), n, l, _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def depth_to_space(self, x, block):
+        self._chk_in(x, 4)
+        n, h, w, c = x.shape
+        out = torch.empty((n, h * block, w * block, max(c // (block * block), 1)), dtype=torch.float32,
+                          device=self.device)
+        check(lib.pfnl_depth_to_space(self._h, _ptr(x), n, h, w, c, block, _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def space_to_depth(self, x, block):
+        self._chk_in(x, 4)
+        n, h, w, c = x.shape
+        out = torch.empty((n, max(h // block, 1), max(w // block, 1), c * block * block), dtype=torch.float32,
+                          device=self.device)
+        check(lib.pfnl_space_to_depth(self._h, _ptr(x), n, h, w, c, block, _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def conv2d(self, x, kernel, bias, act=False, residual=None):
+        self._chk_in(x, 4)
+        self._chk_in(kernel, 4)
+        self._chk_in(bias, 1)
+        n, h, w, ci = x.shape
+        kh, kw, kci, co = kernel.shape
+        if kh != kw or kci != ci:
+            raise ValueError("kernel must be HWIO [k,k,Cin,Cout] matching the input channels")
+        if residual is not None:
+            self._chk_in(residual, 4)
+        out = torch.empty((n, h, w, co), dtype=torch.float32, device=self.device)
+        check(lib.pfnl_conv2d_nhwc(self._h, _ptr(x), n, h, w, ci, _ptr(kernel), _ptr(bias), kh, co, 1 if act else 0,
+                                   _ptr(residual), _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def bicubic4(self, x):
+        self._chk_in(x, 4)
+        n, h, w, c = x.shape
+        out = torch.empty((n, 4 * h, 4 * w, c), dtype=torch.float32, device=self.device)
+        check(lib.pfnl_bicubic4(self._h, _ptr(x), n, h, w, c, _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def pfrb(self, blk, frames, n, h, w):
+        """frames [N*7,H,W,64] -> one Progressive Fusion Residual Block (pfnl.py:66-71)."""
+        self._chk_in(frames, 4)
+        out = torch.empty_like(frames)
+        check(lib.pfnl_pfrb(self._h, blk, _ptr(frames), n, h, w, _ptr(out), _stream_ptr(self.device)))
+        return out
+
+
+# -- image IO with the reference's conventions (utils.py:362-372) ---------------------------
+def cv2_imread(path):
+    import cv2
+    img = cv2.imread(path)
+    if img is None:
+        raise IOError(f"cannot read {path}")
+    if img.ndim == 3:
+        img = img[:, :, ::-1]  # BGR -> RGB
+    return img
+
+
+def cv2_imsave(path, img):
+    import cv2
+    if img.ndim == 3:
+        img = img[:, :, ::-1]  # RGB -> BGR
+    return cv2.imwrite(path, np.ascontiguousarray(img))
+
+
+def automkdir(path):
+    os.makedirs(path, exist_ok=True)
+
+
+def gkern(kernlen=13, nsig=1.6):
+    """utils.py:95-102: 13x13 sigma=1.6 Gaussian (scipy's gaussian_filter of a dirac)."""
+    from scipy.ndimage import gaussian_filter
+    inp = np.zeros((kernlen, kernlen))
+    inp[kernlen // 2, kernlen // 2] = 1
+    return gaussian_filter(inp, nsig)
+
+
+def downsample_4d(imgs, scale=4):
+    """DownSample_4D (utils.py:169-192): REFLECT pad 6, depthwise 13x13 Gaussian, stride `scale`.
+    Host-side for now (input preparation, the step before the hot path)."""
+    blur = gkern(13, 1.6).astype(np.float32)
+    x = np.asarray(imgs, np.float32)
+    xp = np.pad(x, ((0, 0), (6, 6), (6, 6), (0, 0)), mode="reflect")
+    n, hp, wp, c = xp.shape
+    ho, wo = (hp - 13) // scale + 1, (wp - 13) // scale + 1
+    win = np.lib.stride_tricks.sliding_window_view(xp, (13, 13), axis=(1, 2))[:, ::scale, ::scale]
+    win = win[:, :ho, :wo]
+    return np.einsum("nhwcij,ij->nhwc", win, blur, optimize=True).astype(np.float32)
+
+
+class PFNL:
+    """Drop-in for the reference's `PFNL(VSR)` class on the inference path."""
+
+    def __init__(self, weights=None, device=None, precision="fp32", graphs=True):
+        # hyper-parameters kept with the reference's names and values (model/pfnl.py:21-37)
+        self.num_frames = 7
+        self.scale = 4
+        self.in_size = 32
+        self.gt_size = self.in_size * self.scale
+        self.eval_in_size = [128, 240]
+        self.batch_size = 16
+        self.eval_basz = 4
+        self.save_dir = './checkpoint/pfnl'
+        self.log_dir = './pfnl.txt'
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        self.precision = precision
+        self._device = device
+        self._graphs = graphs
+        self._weights = None
+        self._engine = None
+        if weights is not None:
+            self.load_weights(weights)
+
+    # -- weights ---------------------------------------------------------------------------
+    def load_weights(self, weights):
+        """dict {tf_variable_name: array} or a path to an .npz of the same."""
+        if isinstance(weights, (str, os.PathLike)):
+            weights = _weights.load_npz(weights)
+        self._weights = _weights.validate(weights)
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+        return True
+
+    def load(self, checkpoint_dir=None, step=None):
+        """base_model.py:231-243: restore from `save_dir`; returns False (and keeps the
+        initialiser values) when nothing is found.  Reads `<dir>/pfnl.npz`."""
+        d = checkpoint_dir or self.save_dir
+        p = join(d, "pfnl.npz")
+        if os.path.exists(p):
+            print(" [*] Reading checkpoint {}".format(p))
+            self.load_weights(p)
+            return True
+        print(" [!] Reading checkpoints... ERROR (no {}); using Xavier-initialised weights".format(p))
+        return False
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            if self._weights is None:
+                self._weights = _weights.xavier_init()
+            self._engine = Engine(self._weights, self._device, self.precision, self._graphs)
+        return self._engine
+
+    # -- the hot path ----------------------------------------------------------------------
+    def forward(self, x):
+        """x [N,7,H,W,3] float32 in [0,1] -> [N,1,4H,4W,3] (model/pfnl.py:39-80).
+        CUDA tensor in -> CUDA tensor out (asynchronous on the current stream);
+        numpy / CPU tensor in -> same kind out (feed/fetch like sess.run, pfnl.py:252)."""
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            return self.engine.forward(x.to(torch.float32).contiguous())
+        out = self.engine.forward_host(x)
+        return out if isinstance(x, torch.Tensor) else out.numpy()
+
+    def eval_mse(self, sr, hr):
+        """tf.reduce_mean((SR-H)**2, axis=[2,3,4]) (pfnl.py:90) -> [N,1]."""
+        dev = self.engine.device
+        srt = torch.as_tensor(sr, dtype=torch.float32).to(dev).contiguous()
+        hrt = torch.as_tensor(hr, dtype=torch.float32).to(dev).contiguous()
+        m = self.engine.mse(srt, hrt)[:, None]
+        return m if isinstance(sr, torch.Tensor) and sr.is_cuda else m.cpu().numpy()
+
+    @staticmethod
+    def psnr(mse):
+        """10*log10(1/mse) (pfnl.py:139)."""
+        return 10.0 * np.log10(1.0 / np.asarray(mse, dtype=np.float64))
+
+    # -- video harnesses (model/pfnl.py:203-332) -------------------------------------------
+    def _window_list(self, lrs):
+        max_frame = lrs.shape[0]
+        lr_list = []
+        for i in range(max_frame):
+            index = np.array([i for i in range(i - self.num_frames // 2, i + self.num_frames // 2 + 1)])
+            index = np.clip(index, 0, max_frame - 1).tolist()
+            lr_list.append(np.array([lrs[j] for j in index]))
+        return np.array(lr_list)
+
+    def _run_video(self, lrs, save_path, part):
+        max_frame = lrs.shape[0]
+        if max_frame == 0:
+            return np.array([])
+        if part > max_frame:
+            part = max_frame
+        num_once = max_frame // part if max_frame % part == 0 else max_frame // part + 1
+        lr_list = self._window_list(lrs)
+        print('Save at {}'.format(save_path))
+        print('{} Inputs With Shape {}'.format(lrs.shape[0], lrs.shape[1:]))
+        all_time = []
+        for i in range(part):
+            batch = lr_list[i * num_once:(i + 1) * num_once]
+            if batch.shape[0] == 0:
+                break
+            st_time = time.time()
+            sr = self.forward(np.ascontiguousarray(batch, dtype=np.float32))
+            all_time.append(time.time() - st_time)
+            for j in range(sr.shape[0]):
+                img = sr[j][0] * 255.
+                img = np.clip(img, 0, 255)
+                img = np.round(img, 0).astype(np.uint8)
+                cv2_imsave(join(save_path, '{:0>4}.png'.format(i * num_once + j)), img)
+        all_time = np.array(all_time)
+        if max_frame > 0:
+            mean_t = np.mean(all_time[1:]) if all_time.size > 1 else float('nan')
+            print('spent {} s in total and {} s in average'.format(np.sum(all_time), mean_t))
+        return all_time
+
+    def test_video_truth(self, path, name='result', reuse=False, part=50):
+        save_path = join(path, name)
+        automkdir(save_path)
+        inp_path = join(path, 'truth')
+        imgs = sorted(glob.glob(join(inp_path, '*.png')))
+        imgs = np.array([cv2_imread(i) for i in imgs]) / 255.
+        if not reuse and self._weights is None:
+            self.load(self.save_dir)
+        lrs = downsample_4d(imgs, self.scale) if len(imgs) else np.zeros((0, 0, 0, 3), np.float32)
+        return self._run_video(lrs, save_path, part)
+
+    def test_video_lr(self, path, name='result', reuse=False, part=50):
+        save_path = join(path, name)
+        automkdir(save_path)
+        inp_path = join(path, 'blur{}'.format(self.scale))
+        imgs = sorted(glob.glob(join(inp_path, '*.png')))
+        lrs = np.array([cv2_imread(i) for i in imgs]) / 255.
+        if not reuse and self._weights is None:
+            self.load(self.save_dir)
+        return self._run_video(lrs, save_path, part)
+
+    testvideo = test_video_lr  # README.md:31 spelling used by the other models
+
+    def testvideos(self, path='/dev/f/data/video/test2/udm10', start=0, name='pfnl'):
+        kind = sorted(glob.glob(join(path, '*')))
+        kind = [k for k in kind if os.path.isdir(k)]
+        reuse = False
+        for k in kind:
+            idx = kind.index(k)
+            if idx >= start:
+                if idx > start:
+                    reuse = True
+                datapath = join(path, k)
+                self.test_video_truth(datapath, name=name, reuse=reuse, part=1000)

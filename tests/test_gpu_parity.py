@@ -1,0 +1,343 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bars: reorders bit-exact; fp32 path <= 1e-3 max-abs end to end in both weight regimes
+(north_star); other stages at the tolerances written in each test."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pfnl_ref as R
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def engines(built_lib):
+    from pfnl_b200 import Engine
+    return {reg: Engine(R.make_weights(reg), device=0, precision="fp32", graphs=False) for reg in "AB"}
+
+
+def cu(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
+
+
+# ---- reorders: bit exact ------------------------------------------------------------------
+@pytest.mark.parametrize("b,co", [(2, 4), (2, 1), (2, 3), (2, 12), (4, 3), (2, 21), (3, 5)])
+def test_depth_to_space_bit_exact(engines, b, co):
+    e = engines["A"]
+    rng = np.random.default_rng(10)
+    x = rng.standard_normal((3, 5, 7, b * b * co)).astype(np.float32)
+    y = e.depth_to_space(cu(x), b).cpu().numpy()
+    assert np.array_equal(y, R.depth_to_space(x, b))
+    assert np.array_equal(y, R.periodic_shuffle(x, b, co))          # modules/ps.py:_PS
+    back = e.space_to_depth(cu(y), b).cpu().numpy()
+    assert np.array_equal(back, x)
+    assert np.array_equal(back, R.space_to_depth(y, b))
+    if co > 1:
+        crd = torch.pixel_shuffle(torch.from_numpy(x).permute(0, 3, 1, 2), b).permute(0, 2, 3, 1).numpy()
+        assert not np.array_equal(y, crd)
+
+
+def test_depth_to_space_large_and_unaligned(engines):
+    e = engines["A"]
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((16, 32, 32, 48)).astype(np.float32)
+    assert np.array_equal(e.depth_to_space(cu(x), 2).cpu().numpy(), R.depth_to_space(x, 2))
+    # a view whose storage offset breaks 16-byte alignment -> scalar path
+    buf = torch.zeros(2 * 4 * 4 * 12 + 1, device="cuda")
+    v = buf[1:].view(2, 4, 4, 12)
+    xs = rng.standard_normal((2, 4, 4, 12)).astype(np.float32)
+    v.copy_(torch.from_numpy(xs))
+    assert np.array_equal(e.depth_to_space(v, 2).cpu().numpy(), R.depth_to_space(xs, 2))
+
+
+@pytest.mark.parametrize("shape", [(1, 32, 32), (2, 6, 10), (1, 2, 2)])
+def test_pack_tokens_bit_exact(engines, shape):
+    n, h, w = shape
+    x = R.make_input(n, h, w, seed=3)
+    tok = engines["A"].pack_tokens(cu(x)).cpu().numpy()
+    assert np.array_equal(tok.reshape(n, h // 2, w // 2, 84), R.tokens(x))
+
+
+# ---- bicubic --------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(1, 5, 7, 3), (2, 32, 32, 3), (1, 1, 2, 1), (1, 2, 1, 4)])
+def test_bicubic4(engines, shape):
+    rng = np.random.default_rng(12)
+    img = rng.random(shape, dtype=np.float32)
+    out = engines["A"].bicubic4(cu(img)).cpu().numpy()
+    ref = R.resize_bicubic(img, 4 * shape[1], 4 * shape[2])
+    np.testing.assert_allclose(out, ref, atol=1e-6)
+    assert np.array_equal(out[:, ::4, ::4], img)     # phase 0 copies the input pixel exactly
+
+
+def test_bicubic4_golden(engines):
+    z = np.load(os.path.join(GOLD, "bicubic_5x7.npz"))
+    np.testing.assert_allclose(engines["A"].bicubic4(cu(z["img"])).cpu().numpy(), z["out"], atol=1e-6)
+
+
+# ---- convolutions (fp32 FFMA) -------------------------------------------------------------------
+@pytest.mark.parametrize("k,ci,co,h,w,act,res", [
+    (3, 64, 64, 32, 32, True, False),
+    (3, 64, 64, 9, 21, True, True),      # ragged tiles
+    (3, 128, 64, 16, 16, True, True),    # conv2 shape
+    (1, 448, 64, 10, 6, True, False),    # conv10 shape
+    (3, 448, 48, 8, 8, True, False),     # convmerge1 shape
+    (3, 12, 12, 12, 12, False, False),   # convmerge2 shape (direct kernel)
+    (5, 3, 64, 11, 13, True, False),     # conv0 shape (direct kernel)
+    (3, 16, 4, 3, 3, False, False),
+])
+def test_conv2d_vs_oracle(engines, k, ci, co, h, w, act, res):
+    rng = np.random.default_rng(100 + k + ci + co + h)
+    x = rng.standard_normal((2, h, w, ci)).astype(np.float32)
+    ker = (rng.standard_normal((k, k, ci, co)) / np.sqrt(k * k * ci)).astype(np.float32)
+    b = rng.standard_normal(co).astype(np.float32)
+    r = rng.standard_normal((2, h, w, co)).astype(np.float32) if res else None
+    y = engines["A"].conv2d(cu(x), cu(ker), cu(b), act=act, residual=cu(r) if res else None).cpu().numpy()
+    ref = R.conv2d_same(x.astype(np.float64), ker.astype(np.float64), b.astype(np.float64), act=act)
+    if res:
+        ref = ref + r
+    np.testing.assert_allclose(y, ref, atol=2e-5, rtol=0)
+    # borders (zero 'same' padding) checked separately
+    np.testing.assert_allclose(y[:, [0, -1]], ref[:, [0, -1]], atol=2e-5, rtol=0)
+    np.testing.assert_allclose(y[:, :, [0, -1]], ref[:, :, [0, -1]], atol=2e-5, rtol=0)
+
+
+def test_conv_lrelu_slope(engines):
+    # all-negative pre-activations: output must be exactly 0.2 * pre-activation
+    x = np.ones((1, 4, 4, 16), np.float32)
+    ker = np.zeros((1, 1, 16, 4), np.float32)
+    ker[0, 0, 0, :] = -1.0
+    b = np.zeros(4, np.float32)
+    y = engines["A"].conv2d(cu(x), cu(ker), cu(b), act=True).cpu().numpy()
+    np.testing.assert_allclose(y, -0.2, atol=1e-7)
+
+
+# ---- non-local block ------------------------------------------------------------------------------
+@pytest.mark.parametrize("hh,ww,n", [(8, 8, 2), (16, 16, 2), (10, 6, 2), (13, 10, 1), (32, 32, 1), (1, 1, 1)])
+def test_nonlocal_vs_oracle_fp64(engines, hh, ww, n):
+    W = R.make_weights("B")
+    P = "nlvsr/nlblock_0/"
+    rng = np.random.default_rng(hh * 100 + ww)
+    t = rng.random((n, hh, ww, 84), dtype=np.float32)
+    ref = R.nonlocal_block(t.astype(np.float64), *(W[P + s].astype(np.float64) for s in
+                                                   ("g/g/kernel", "g/g/bias", "w/w/kernel", "w/w/bias")), stable=True)
+    out = engines["B"].nonlocal_block(cu(t.reshape(n, hh * ww, 84))).cpu().numpy().reshape(n, hh, ww, 84)
+    np.testing.assert_allclose(out, ref, atol=2e-5, rtol=0)
+
+
+def test_nonlocal_golden_and_large_logits(engines):
+    for name in ["nonlocal_10x6.npz", "nonlocal_16x16.npz"]:
+        z = np.load(os.path.join(GOLD, name))
+        n, hh, ww, _ = z["t"].shape
+        out = engines["B"].nonlocal_block(cu(z["t"].reshape(n, hh * ww, 84))).cpu().numpy()
+        np.testing.assert_allclose(out.reshape(z["z"].shape), z["z"], atol=2e-5)
+    # bright flat input (all 0.9): logits 68, the naive exp/sum would overflow for large L; the
+    # streamed softmax must stay finite and equal the uniform average
+    W = R.make_weights("B")
+    P = "nlvsr/nlblock_0/"
+    t = np.full((1, 2048, 84), 0.9, np.float32)
+    out = engines["B"].nonlocal_block(cu(t)).cpu().numpy()
+    assert np.isfinite(out).all()
+    g = t[0, :1] @ W[P + "g/g/kernel"][0, 0] + W[P + "g/g/bias"]
+    zrow = g @ W[P + "w/w/kernel"][0, 0] + W[P + "w/w/bias"]
+    np.testing.assert_allclose(out[0], np.broadcast_to(zrow, (2048, 84)), atol=1e-4)
+
+
+def test_nonlocal_6480_tokens(engines):
+    """Vid4 'calendar'-sized token grid (90x72 -> L=6480, not a multiple of any tile)."""
+    W = R.make_weights("B")
+    P = "nlvsr/nlblock_0/"
+    rng = np.random.default_rng(9)
+    t = (rng.random((1, 6480, 84), dtype=np.float32) * 0.5).astype(np.float32)
+    out = engines["B"].nonlocal_block(cu(t)).cpu().numpy()
+    rows = [0, 1234, 6479]
+    x64 = t[0].astype(np.float64)
+    s = x64[rows] @ x64.T
+    p = np.exp(s - s.max(1, keepdims=True))
+    p /= p.sum(1, keepdims=True)
+    g = x64 @ W[P + "g/g/kernel"][0, 0].astype(np.float64) + W[P + "g/g/bias"]
+    ref = (p @ g) @ W[P + "w/w/kernel"][0, 0].astype(np.float64) + W[P + "w/w/bias"]
+    np.testing.assert_allclose(out[0, rows], ref, atol=2e-5)
+
+
+# ---- one PFRB and the whole forward -----------------------------------------------------------------
+def test_single_pfrb_vs_oracle(engines):
+    n, h, w = 1, 12, 20
+    W = R.make_weights("B")
+    rng = np.random.default_rng(21)
+    fr = rng.standard_normal((n * 7, h, w, 64)).astype(np.float32)
+    out = engines["B"].pfrb(3, cu(fr), n, h, w).cpu().numpy()
+    P = "nlvsr/"
+    f64 = fr.astype(np.float64)
+    k = lambda s: W[P + s].astype(np.float64)
+    inp1 = [R.conv2d_same(f64[t:t + 1], k("conv1_3/kernel"), k("conv1_3/bias"), act=True) for t in range(7)]
+    base = R.conv2d_same(np.concatenate(inp1, -1), k("conv10_3/kernel"), k("conv10_3/bias"), act=True)
+    ref = np.concatenate([f64[t:t + 1] + R.conv2d_same(np.concatenate([base, inp1[t]], -1), k("conv2_3/kernel"),
+                                                       k("conv2_3/bias"), act=True) for t in range(7)], 0)
+    np.testing.assert_allclose(out, ref, atol=5e-5, rtol=0)
+
+
+@pytest.mark.parametrize("regime", ["A", "B"])
+@pytest.mark.parametrize("shape", [(1, 8, 8), (2, 6, 10)])
+def test_forward_small_vs_oracle_and_golden(engines, regime, shape):
+    n, h, w = shape
+    z = np.load(os.path.join(GOLD, f"forward_{regime}_{n}x{h}x{w}.npz"))
+    x = R.make_input(n, h, w)
+    assert np.array_equal(x, z["x"])
+    y = engines[regime].forward(cu(x)).cpu().numpy()
+    assert y.shape == (n, 1, 4 * h, 4 * w, 3)
+    ref64 = R.pfnl_forward(x, R.make_weights(regime), dtype=np.float64)
+    assert np.abs(y - ref64).max() <= 1e-3
+    assert np.abs(y - z["y64"]).max() <= 1e-3
+    assert np.abs(y - z["y"]).max() <= 1e-3
+
+
+@pytest.mark.parametrize("regime", ["A", "B"])
+def test_forward_pr1_parity_gate(engines, regime):
+    """BASELINE config 1: 1 clip x 7 x 32x32x3 -> 128x128x3, <= 1e-3 max-abs vs the fp32 oracle
+    (and vs the fp64 evaluation) in both weight regimes."""
+    x = R.make_input(1, 32, 32)
+    W = R.make_weights(regime)
+    y = engines[regime].forward(cu(x)).cpu().numpy()
+    ref32 = R.pfnl_forward(x, W, dtype=np.float32)
+    ref64 = np.load(os.path.join(GOLD, f"forward_{regime}_1x32x32.npz"))["y64"]
+    e32, e64 = np.abs(y - ref32).max(), np.abs(y - ref64).max()
+    print(f"regime {regime}: |out|max={np.abs(ref64).max():.3f} max-abs vs fp32 oracle {e32:.3e}, vs fp64 {e64:.3e}")
+    assert e32 <= 1e-3 and e64 <= 1e-3
+
+
+def test_forward_batch16_matches_per_clip(engines):
+    """Clips are independent: a batch of 16 equals 16 single-clip forwards bit for bit."""
+    x = R.make_input(16, 32, 32, seed=99)
+    e = engines["B"]
+    yb = e.forward(cu(x)).cpu().numpy()
+    for i in (0, 7, 15):
+        yi = e.forward(cu(x[i:i + 1])).cpu().numpy()
+        assert np.array_equal(yb[i:i + 1], yi)
+    ref = R.pfnl_forward(x[:2], R.make_weights("B"), backend="torch")
+    assert np.abs(yb[:2] - ref).max() <= 1e-3
+
+
+def test_forward_128x128_properties(engines):
+    """BASELINE config 4 size (L=4096): finite, right shape, and the skip path is visible:
+    with all conv weights zeroed the output is exactly the bicubic of the centre frame."""
+    from pfnl_b200 import Engine
+    x = R.make_input(1, 128, 128, seed=5)
+    y = engines["B"].forward(cu(x))
+    assert y.shape == (1, 1, 512, 512, 3) and torch.isfinite(y).all()
+    ref = R.pfnl_forward(x, R.make_weights("B"), backend="torch")
+    assert np.abs(y.cpu().numpy() - ref).max() <= 1e-3
+    Wz = {k: np.zeros_like(v) for k, v in R.make_weights("A").items()}
+    ez = Engine(Wz, 0, "fp32", graphs=False)
+    yz = ez.forward(cu(x)).cpu().numpy()
+    np.testing.assert_allclose(yz[:, 0], R.resize_bicubic(x[:, 3], 512, 512), atol=1e-6)
+    ez.close()
+
+
+# ---- MSE / PSNR ---------------------------------------------------------------------------------------
+def test_mse_vs_oracle(engines):
+    rng = np.random.default_rng(31)
+    sr = rng.random((5, 1, 32, 24, 3), dtype=np.float32)
+    hr = rng.random((5, 1, 32, 24, 3), dtype=np.float32)
+    m = engines["A"].mse(cu(sr), cu(hr)).cpu().numpy()
+    np.testing.assert_allclose(m, R.mse_per_clip(sr, hr)[:, 0], rtol=1e-6)
+
+
+# ---- boundary behaviour -------------------------------------------------------------------------------
+def test_errors_and_ownership(engines):
+    from pfnl_b200 import _lib
+    e = engines["A"]
+    with pytest.raises(_lib.PfnlError) as ei:
+        e.forward(torch.zeros(1, 7, 7, 8, 3, device="cuda"))     # odd H
+    assert ei.value.code == _lib.ERR_BAD_SHAPE
+    with pytest.raises(ValueError):
+        e.forward(torch.zeros(1, 6, 8, 8, 3, device="cuda"))     # T != 7
+    with pytest.raises(ValueError):
+        e.forward(torch.zeros(1, 7, 8, 8, 3))                    # not on the device
+    with pytest.raises(_lib.PfnlError):
+        e.depth_to_space(torch.zeros(1, 2, 2, 6, device="cuda"), 2)
+    # NULL handle / pointer -> error code, not a crash
+    assert _lib.lib.pfnl_forward(None, None, 1, 8, 8, None, None) == _lib.ERR_BAD_ARG
+    assert _lib.lib.pfnl_workspace_bytes(0, 16, 32, 32) > 16 * 7 * 32 * 32 * 64 * 4 * 2
+    # create / destroy repeatedly: no leak of device memory
+    from pfnl_b200 import Engine
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(3):
+        t = Engine(R.make_weights("A"), 0, "fp32")
+        t.forward(torch.rand(1, 7, 8, 8, 3, device="cuda"))
+        torch.cuda.synchronize()
+        t.close()
+    assert abs(torch.cuda.mem_get_info()[0] - free0) < 64 << 20
+
+
+def test_graph_replay_and_stream_async(built_lib):
+    from pfnl_b200 import Engine
+    W = R.make_weights("B")
+    eg = Engine(W, 0, "fp32", graphs=True)
+    ep = Engine(W, 0, "fp32", graphs=False)
+    x = cu(R.make_input(2, 16, 16))
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        out = torch.empty(2, 1, 64, 64, 3, device="cuda")
+        l0 = eg.launches
+        for _ in range(3):
+            eg.forward(x, out=out)          # captured once, replayed
+        per = (eg.launches - l0) // 3
+        assert per >= 60
+    s.synchronize()
+    assert torch.equal(out, ep.forward(x))
+    # user-side capture of pfnl_forward (workspace reserved beforehand)
+    ep.reserve(2, 16, 16)
+    g = torch.cuda.CUDAGraph()
+    out2 = torch.empty_like(out)
+    with torch.cuda.graph(g):
+        ep.forward(x, out=out2)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out)
+    eg.close()
+    ep.close()
+
+
+def test_host_path_matches_device_path(engines):
+    from pfnl_b200 import PFNL
+    x = R.make_input(3, 8, 12)
+    m = PFNL(weights=R.make_weights("B"), precision="fp32")
+    y_host = m.forward(x.astype(np.float64))             # float64 numpy in, like pfnl.py:209,252
+    assert isinstance(y_host, np.ndarray) and y_host.dtype == np.float32
+    y_dev = m.forward(cu(x))
+    assert torch.equal(torch.from_numpy(y_host).cuda(), y_dev)
+    assert m.eval_mse(y_host, y_host * 0).shape == (3, 1)
+
+
+def test_test_video_lr_call_surface(tmp_path, engines):
+    """test_video_lr on a synthetic 10-frame PNG directory: window clamping, file naming,
+    uint8 rounding and BGR write (model/pfnl.py:264-320, utils.py:362-366)."""
+    import cv2
+    from pfnl_b200 import PFNL
+    rng = np.random.default_rng(41)
+    d = tmp_path / "vid" / "blur4"
+    d.mkdir(parents=True)
+    frames = rng.integers(0, 256, size=(10, 8, 12, 3), dtype=np.uint8)
+    for i, f in enumerate(frames):
+        cv2.imwrite(str(d / f"{i:04d}.png"), f[:, :, ::-1])
+    W = R.make_weights("B")
+    m = PFNL(weights=W, precision="fp32")
+    times = m.test_video_lr(str(tmp_path / "vid"), name="out", part=50)
+    assert len(times) == 10
+    outs = sorted(os.listdir(tmp_path / "vid" / "out"))
+    assert outs == [f"{i:04d}.png" for i in range(10)]
+    lrs = frames.astype(np.float64) / 255.
+    for i in (0, 4, 9):
+        clip = np.stack([lrs[j] for j in R.window_indices(10, i)])[None].astype(np.float32)
+        ref = R.quantise_uint8(R.pfnl_forward(clip, W)[0, 0])
+        got = cv2.imread(str(tmp_path / "vid" / "out" / f"{i:04d}.png"))[:, :, ::-1]
+        assert got.shape == (32, 48, 3)
+        assert np.abs(got.astype(int) - ref.astype(int)).max() <= 1     # rounding ties only
+        assert (got != ref).mean() < 0.01
+    # part < max_frame batches several clips per run (num_once = ceil(10/4) = 3)
+    times = m.testvideo(str(tmp_path / "vid"), name="out2", part=4)
+    assert sorted(os.listdir(tmp_path / "vid" / "out2")) == outs
