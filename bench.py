@@ -101,15 +101,43 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def effective_cpus():
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(p) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_reference_run(clips, size, steps, warmup, budget_s=None):
     """Times the CPU restatement of the reference graph (oracle, torch-CPU back-end, all host
     threads).  TensorFlow 1.12 itself cannot be installed in this image."""
     import torch
     from oracle import pfnl_ref as R
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     W = R.make_weights("A")
     x = R.make_input(clips, size, size)
+    # "all the host threads it can use": the usable count is bounded by affinity and the cgroup
+    # quota, and oneDNN on many-core hosts is often fastest below that; pick the best of a few
+    # candidates on a 2-clip trial (cheap) so the baseline is not handicapped by oversubscription.
+    avail = effective_cpus()
+    cands = sorted({c for c in (avail, max(1, avail // 2), 64, 32, 16, 8) if 1 <= c <= avail}, reverse=True)
+    best, cores = None, avail
+    for c in cands:
+        torch.set_num_threads(c)
+        R.pfnl_forward(x[:2], W, backend="torch")
+        t0 = time.perf_counter()
+        R.pfnl_forward(x[:2], W, backend="torch")
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, cores = dt, c
+    torch.set_num_threads(cores)
     t0 = time.perf_counter()
     R.pfnl_forward(x, W, backend="torch")
     first = time.perf_counter() - t0
@@ -131,7 +159,8 @@ def cpu_reference_run(clips, size, steps, warmup, budget_s=None):
     value = sample_clips * HR_PX_PER_CLIP(size, size) / mean_s
     return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{len(times)} timed forwards of {sample_clips} clips x 7x{size}x{size} (torch-CPU/oneDNN fp32 "
-                      f"restatement of the TF1 graph, {cores} threads; TF 1.12 not installable)",
+                      f"restatement of the TF1 graph, {cores} threads = fastest of {cands} on this host with "
+                      f"{avail} usable CPUs; TF 1.12 not installable)",
             "ms_per_step": mean_s * 1e3, "steps": len(times)}
 
 

@@ -1,0 +1,725 @@
+// Tensor-core convolutions of the PFRB stack (model/pfnl.py:65-74) for sm_100a:
+// TMA -> shared memory -> tcgen05.mma (fp16 operands, fp32 accumulators in TMEM) -> fused epilogue.
+//
+// Data layout in HBM: activations are fp16 NHWC planes [images, H, W, 64] (one pixel = one
+// 128-byte row = one 128B-swizzle row).  PFNL_PREC_TC_FP16 keeps one plane per tensor;
+// PFNL_PREC_TC_FP16X3 keeps two (hi = fp16(v), lo = fp16((v-hi)*2048)) and runs three MMAs per
+// k-step (hi*hi into D0; hi*lo' + lo'*hi into D1; result D0 + D1/2048), which carries ~22
+// mantissa bits through the fp16 tensor pipe.
+//
+// Implicit GEMM: M = 128 output pixels (a 16-row x 8-column spatial tile of one image),
+// N = 64 (48 for convmerge1) output channels, K = taps x 64 input channels.  Per tile ONE TMA
+// box {64 ch, BOX_W px, 18 rows} (out-of-bounds zero fill == 'same' zero padding) lands a halo
+// patch in smem; the A operand of tap (dy,dx) is the same patch addressed through a UMMA
+// descriptor whose start is shifted by (dy*BOX_W+dx) 128-byte rows and whose 8-row-group stride
+// (SBO) is BOX_W*128 - so each input byte is fetched from L2 once per tile, not 9 times.
+// Weights ([taps][N][64] fp16, pre-swizzled) stay resident in smem for the CTA's lifetime.
+//
+// Warp roles (192 threads, 1 CTA / SM, persistent over tiles): warp 0 = TMA producer, warp 1 =
+// MMA issuer (one elected lane), warps 2-5 = epilogue (tcgen05.ld -> bias / leaky_relu / partial
+// sums / residual -> fp16 planes or fp32).  TMEM accumulators are double buffered so the
+// epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tc.h"
+#include "tc_ptx.cuh"
+#include "tc_tmap.h"
+
+namespace pfnl {
+
+using namespace tc;
+
+enum TcEpi {
+  kEpiActPlanes = 0,   // v = lrelu(acc + bias)                        -> fp16 planes
+  kEpiPartialF32 = 1,  // v = acc (+ previous content if accumulate)   -> fp32
+  kEpiResPlanes = 2,   // v = lrelu(acc + pbase + bias) + residual     -> fp16 planes (may alias residual)
+  kEpiFinalF32 = 3     // v = lrelu(acc + previous + bias)             -> fp32
+};
+
+struct TcConvParams {
+  int H, W, tiles_x, tiles_y, n_tiles;
+  int img_mul, img_add;  // source image coordinate of stage s = out_img*img_mul + img_add + s
+  int epi;
+  int accumulate;        // kEpiPartialF32: add the previous content of out_f32
+  int pb_div;            // pbase image index = out_img / pb_div
+  int base_offset_mode;  // UMMA descriptor base-offset field: 0 -> 0, 1 -> (start>>7)&7
+  const float* bias;     // [NOUT]
+  const float* pbase;    // fp32 [out_img/pb_div][H][W][64]
+  __half* out_hi;
+  __half* out_lo;
+  const __half* res_hi;
+  const __half* res_lo;
+  float* out_f32;        // [out_images][H][W][NOUT]
+};
+
+template <int KS, int NSRC, int NSPLIT, int NOUT>
+struct TcCfg {
+  static constexpr int TAPS = KS * KS;
+  static constexpr int NTAPS = NSRC * TAPS;
+  static constexpr int BOX_W = KS == 3 ? kTcPatchW3 : 8;
+  static constexpr int BOX_H = KS == 3 ? 18 : 16;
+  static constexpr int PATCH_BYTES = BOX_W * BOX_H * 128;
+  static constexpr int SLOT_BYTES = (PATCH_BYTES + 1023) / 1024 * 1024;
+  static constexpr int WT_BYTES = NOUT * 128;
+  static constexpr int W_BYTES = NSPLIT * NTAPS * WT_BYTES;
+  static constexpr int SMEM_MAX = 227 * 1024;
+  static constexpr int CTRL_BYTES = 1024;
+  static constexpr int BUDGET = SMEM_MAX - 1024 /*align slack*/ - CTRL_BYTES - W_BYTES;
+  static constexpr int TOTAL_SLOTS = BUDGET / SLOT_BYTES;
+  static constexpr int NL = NSPLIT == 1 ? 0 : (TOTAL_SLOTS / 2 > 3 ? 3 : TOTAL_SLOTS / 2);
+  static constexpr int NH = (TOTAL_SLOTS - NL) > 4 ? 4 : (TOTAL_SLOTS - NL);
+  static constexpr int SMEM_BYTES = 1024 + CTRL_BYTES + W_BYTES + (NH + NL) * SLOT_BYTES;
+  static constexpr int TMEM_BUF_COLS = NSPLIT * 64;
+  static constexpr int TMEM_COLS = 2 * TMEM_BUF_COLS;  // 128 or 256 (power of two)
+  static_assert(NH >= 1 && (NSPLIT == 1 || NL >= 1), "shared memory budget too small");
+  static_assert(SMEM_BYTES <= SMEM_MAX, "shared memory overflow");
+};
+
+struct TcCtrl {
+  uint64_t wfull;
+  uint64_t full_hi[4], empty_hi[4];
+  uint64_t full_lo[4], empty_lo[4];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+  float bias[64];
+};
+
+__device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn((v - __half2float(hi)) * 2048.f);
+}
+
+template <int KS, int NSRC, int NSPLIT, int NOUT>
+__global__ void __launch_bounds__(192, 1)
+    conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                   const __half* __restrict__ wimg, const TcConvParams p) {
+  using C = TcCfg<KS, NSRC, NSPLIT, NOUT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* wsm = smem;                                  // [NSPLIT][NTAPS][WT_BYTES]
+  uint8_t* ring_hi = wsm + C::W_BYTES;                  // [NH][SLOT_BYTES]
+  uint8_t* ring_lo = ring_hi + C::NH * C::SLOT_BYTES;   // [NL][SLOT_BYTES]
+  TcCtrl* ctl = reinterpret_cast<TcCtrl*>(ring_lo + C::NL * C::SLOT_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int PAD = (KS - 1) / 2;
+
+  if (tid == 0) {
+    mbar_init(&ctl->wfull, 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&ctl->full_hi[i], 1);
+      mbar_init(&ctl->empty_hi[i], 1);
+      mbar_init(&ctl->full_lo[i], 1);
+      mbar_init(&ctl->empty_lo[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctl->tmem_full[i], 1);
+      mbar_init(&ctl->tmem_empty[i], 4);
+    }
+    fence_mbar_init();
+    fence_proxy_async();
+    tma_prefetch_desc(&tm_hi);
+    if (NSPLIT == 2) tma_prefetch_desc(&tm_lo);
+  }
+  if (tid < 64) ctl->bias[tid] = (p.bias != nullptr && tid < NOUT) ? p.bias[tid] : 0.f;
+  if (warp == 1) {
+    tmem_alloc(&ctl->tmem_base, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&ctl->wfull, C::W_BYTES);
+      for (int off = 0; off < C::W_BYTES; off += 32768) {
+        const int n = (C::W_BYTES - off) < 32768 ? (C::W_BYTES - off) : 32768;
+        bulk_load(wsm + off, reinterpret_cast<const uint8_t*>(wimg) + off, n, &ctl->wfull);
+      }
+      int sh = 0, ph = 0, sl = 0, pl = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int tx = tile % p.tiles_x;
+        const int r = tile / p.tiles_x;
+        const int ty = r % p.tiles_y;
+        const int img = r / p.tiles_y;
+        const int x0 = tx * 8 - PAD, y0 = ty * 16 - PAD;
+        for (int s = 0; s < NSRC; ++s) {
+          const int ic = img * p.img_mul + p.img_add + s;
+          if (NSPLIT == 2) {
+            mbar_wait(&ctl->empty_lo[sl], pl ^ 1);
+            mbar_arrive_expect_tx(&ctl->full_lo[sl], C::PATCH_BYTES);
+            tma_load_4d(ring_lo + sl * C::SLOT_BYTES, &tm_lo, &ctl->full_lo[sl], 0, x0, y0, ic);
+            if (++sl == C::NL) {
+              sl = 0;
+              pl ^= 1;
+            }
+          }
+          mbar_wait(&ctl->empty_hi[sh], ph ^ 1);
+          mbar_arrive_expect_tx(&ctl->full_hi[sh], C::PATCH_BYTES);
+          tma_load_4d(ring_hi + sh * C::SLOT_BYTES, &tm_hi, &ctl->full_hi[sh], 0, x0, y0, ic);
+          if (++sh == C::NH) {
+            sh = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, NOUT);
+      constexpr uint32_t SBO_A = C::BOX_W * 128;
+      constexpr uint32_t SBO_B = 1024;
+      const uint32_t w_hi = smem_u32(wsm);
+      const uint32_t w_lo = w_hi + C::NTAPS * C::WT_BYTES;
+      mbar_wait(&ctl->wfull, 0);
+      fence_after_sync();
+      int sh = 0, ph = 0, sl = 0, pl = 0, it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&ctl->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+        fence_after_sync();
+        const uint32_t d0 = tmem + buf * C::TMEM_BUF_COLS;
+        const uint32_t d1 = d0 + 64;
+        uint32_t acc0 = 0, acc1 = 0;
+        for (int s = 0; s < NSRC; ++s) {
+          if (NSPLIT == 2) {
+            // lo-plane pass first: its patch slot is released early and refilled under the hi pass
+            mbar_wait(&ctl->full_lo[sl], pl);
+            fence_after_sync();
+            const uint32_t a_base = smem_u32(ring_lo + sl * C::SLOT_BYTES);
+#pragma unroll
+            for (int t = 0; t < C::TAPS; ++t) {
+              const uint32_t shift = ((t / KS) * C::BOX_W + (t % KS)) * 128;
+              const uint32_t wt = w_hi + (s * C::TAPS + t) * C::WT_BYTES;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t a = a_base + shift + k * 32;
+                const uint32_t bo = p.base_offset_mode ? ((a >> 7) & 7) : 0;
+                mma_f16(d1, make_sdesc_sw128(a, SBO_A, bo), make_sdesc_sw128(wt + k * 32, SBO_B, 0), idesc, acc1);
+                acc1 = 1;
+              }
+            }
+            mma_commit(&ctl->empty_lo[sl]);
+            if (++sl == C::NL) {
+              sl = 0;
+              pl ^= 1;
+            }
+          }
+          mbar_wait(&ctl->full_hi[sh], ph);
+          fence_after_sync();
+          const uint32_t a_base = smem_u32(ring_hi + sh * C::SLOT_BYTES);
+#pragma unroll
+          for (int t = 0; t < C::TAPS; ++t) {
+            const uint32_t shift = ((t / KS) * C::BOX_W + (t % KS)) * 128;
+            const uint32_t wt = w_hi + (s * C::TAPS + t) * C::WT_BYTES;
+            const uint32_t wl = w_lo + (s * C::TAPS + t) * C::WT_BYTES;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t a = a_base + shift + k * 32;
+              const uint32_t bo = p.base_offset_mode ? ((a >> 7) & 7) : 0;
+              const uint64_t ad = make_sdesc_sw128(a, SBO_A, bo);
+              mma_f16(d0, ad, make_sdesc_sw128(wt + k * 32, SBO_B, 0), idesc, acc0);
+              acc0 = 1;
+              if (NSPLIT == 2) {
+                mma_f16(d1, ad, make_sdesc_sw128(wl + k * 32, SBO_B, 0), idesc, acc1);
+                acc1 = 1;
+              }
+            }
+          }
+          mma_commit(&ctl->empty_hi[sh]);
+          if (++sh == C::NH) {
+            sh = 0;
+            ph ^= 1;
+          }
+        }
+        mma_commit(&ctl->tmem_full[buf]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;        // row of the tile = TMEM lane
+    const int my = m >> 3, mx = m & 7;  // pixel inside the 16x8 tile
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int tx = tile % p.tiles_x;
+      const int r = tile / p.tiles_x;
+      const int ty = r % p.tiles_y;
+      const int img = r / p.tiles_y;
+      const int y = ty * 16 + my, x = tx * 8 + mx;
+      const bool inb = y < p.H && x < p.W;
+      const long long pix = ((long long)img * p.H + y) * p.W + x;
+      mbar_wait(&ctl->tmem_full[buf], (it >> 1) & 1);
+      fence_after_sync();
+      const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + buf * C::TMEM_BUF_COLS;
+#pragma unroll
+      for (int c0 = 0; c0 < NOUT; c0 += 16) {
+        uint32_t r0[16], r1[16];
+        tmem_ld_32x32b_x16(t0 + c0, r0);
+        if (NSPLIT == 2) tmem_ld_32x32b_x16(t0 + 64 + c0, r1);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          v[j] = __uint_as_float(r0[j]);
+          if (NSPLIT == 2) v[j] = fmaf(__uint_as_float(r1[j]), 1.f / 2048.f, v[j]);
+        }
+        if (inb) {
+          if (p.epi == kEpiActPlanes || p.epi == kEpiResPlanes) {
+            if (p.epi == kEpiResPlanes) {
+              const float4* pb = reinterpret_cast<const float4*>(
+                  p.pbase + (((long long)(img / p.pb_div) * p.H + y) * p.W + x) * 64 + c0);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 t = pb[j4];
+                v[4 * j4 + 0] += t.x;
+                v[4 * j4 + 1] += t.y;
+                v[4 * j4 + 2] += t.z;
+                v[4 * j4 + 3] += t.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = lrelu(v[j] + ctl->bias[c0 + j]);
+            if (p.epi == kEpiResPlanes) {
+              const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + pix * 64 + c0);
+              const uint4 a0 = rh[0], a1 = rh[1];
+              const __half* hh0 = reinterpret_cast<const __half*>(&a0);
+              const __half* hh1 = reinterpret_cast<const __half*>(&a1);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[j] += __half2float(hh0[j]);
+                v[8 + j] += __half2float(hh1[j]);
+              }
+              if (NSPLIT == 2) {
+                const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + pix * 64 + c0);
+                const uint4 b0 = rl[0], b1 = rl[1];
+                const __half* hl0 = reinterpret_cast<const __half*>(&b0);
+                const __half* hl1 = reinterpret_cast<const __half*>(&b1);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  v[j] = fmaf(__half2float(hl0[j]), 1.f / 2048.f, v[j]);
+                  v[8 + j] = fmaf(__half2float(hl1[j]), 1.f / 2048.f, v[8 + j]);
+                }
+              }
+            }
+            __align__(16) __half oh[16];
+            __align__(16) __half ol[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (NSPLIT == 2)
+                split_half(v[j], oh[j], ol[j]);
+              else
+                oh[j] = __float2half_rn(v[j]);
+            }
+            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + pix * 64 + c0);
+            dh[0] = reinterpret_cast<const uint4*>(oh)[0];
+            dh[1] = reinterpret_cast<const uint4*>(oh)[1];
+            if (NSPLIT == 2) {
+              uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * 64 + c0);
+              dl[0] = reinterpret_cast<const uint4*>(ol)[0];
+              dl[1] = reinterpret_cast<const uint4*>(ol)[1];
+            }
+          } else {
+            float4* o = reinterpret_cast<float4*>(p.out_f32 + pix * NOUT + c0);
+            if ((p.epi == kEpiPartialF32 && p.accumulate) || p.epi == kEpiFinalF32) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 t = o[j4];
+                v[4 * j4 + 0] += t.x;
+                v[4 * j4 + 1] += t.y;
+                v[4 * j4 + 2] += t.z;
+                v[4 * j4 + 3] += t.w;
+              }
+            }
+            if (p.epi == kEpiFinalF32) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = lrelu(v[j] + ctl->bias[c0 + j]);
+            }
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) o[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+          }
+        }
+      }
+      // all tcgen05.ld of this warp have completed (wait::ld above): hand the TMEM buffer back
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->tmem_empty[buf]);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, C::TMEM_COLS);
+}
+
+// ---- weight images ------------------------------------------------------------------------------------
+// HWIO fp32 [taps][cin_total][cout] -> [plane][tap][NOUT rows][64 ci] fp16, rows K-major and
+// pre-swizzled (128B) so a linear bulk copy lands them UMMA-ready.  Uses input channels
+// ci_off..ci_off+63.  plane 1 (nsplit=2) holds (w - fp16(w)) * 2048.
+__global__ void pack_tc_weights_kernel(const float* __restrict__ hwio, int taps, int cin_total, int ci_off, int cout,
+                                       int nrows, int nsplit, __half* __restrict__ out, size_t lo_plane_offset) {
+  const int total = taps * nrows * 64;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int ci = e & 63;
+    const int row = (e >> 6) % nrows;
+    const int tap = e / (64 * nrows);
+    const float w = row < cout ? hwio[((long long)tap * cin_total + ci_off + ci) * cout + row] : 0.f;
+    const __half hi = __float2half_rn(w);
+    const uint32_t off = sw128_offset(row, ci >> 3) + (ci & 7) * 2;
+    uint8_t* base = reinterpret_cast<uint8_t*>(out) + (size_t)tap * nrows * 128;
+    *reinterpret_cast<__half*>(base + off) = hi;
+    if (nsplit == 2) {
+      const __half lo = __float2half_rn((w - __half2float(hi)) * 2048.f);
+      *reinterpret_cast<__half*>(base + lo_plane_offset + off) = lo;
+    }
+  }
+}
+
+// fp32 NHWC [.., 64] <-> fp16 planes
+__global__ void f32_to_planes_kernel(const float* __restrict__ in, long long n, int nsplit, __half* __restrict__ hi,
+                                     __half* __restrict__ lo) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const float v = in[e];
+    if (nsplit == 2) {
+      __half h, l;
+      split_half(v, h, l);
+      hi[e] = h;
+      lo[e] = l;
+    } else {
+      hi[e] = __float2half_rn(v);
+    }
+  }
+}
+__global__ void planes_to_f32_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, long long n,
+                                     int nsplit, float* __restrict__ out) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    float v = __half2float(hi[e]);
+    if (nsplit == 2) v = fmaf(__half2float(lo[e]), 1.f / 2048.f, v);
+    out[e] = v;
+  }
+}
+
+// conv0 (5x5, 3->64, leaky_relu; model/pfnl.py:48,61-62) writing fp16 planes.  K = 75 is too
+// small/odd for the MMA path (0.2 % of the FLOPs): CUDA cores, same structure as conv0_kernel.
+template <int NSPLIT>
+__global__ void __launch_bounds__(256) conv0_planes_kernel(const float* __restrict__ inp21, int H, int W,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  __shared__ __align__(16) float wsm[75 * 64];
+  __shared__ float patch[20 * 20 * 3];
+  const int tid = threadIdx.x;
+  const int tiles_x = ceil_div(W, 16);
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x % tiles_x;
+  const int img = blockIdx.y;
+  const int n = img / kFrames, t = img % kFrames;
+  const int y0 = ty * 16, x0 = tx * 16;
+  for (int i = tid; i < 75 * 64; i += 256) wsm[i] = w[i];
+  for (int i = tid; i < 20 * 20 * 3; i += 256) {
+    int c = i % 3, pp = i / 3;
+    int py = pp / 20, px = pp % 20;
+    int gy = y0 + py - 2, gx = x0 + px - 2;
+    float v = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = inp21[(((long long)n * H + gy) * W + gx) * 21 + t * 3 + c];
+    patch[i] = v;
+  }
+  __syncthreads();
+  const int py = tid >> 4, px = tid & 15;
+  float acc[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+#pragma unroll 1
+  for (int dy = 0; dy < 5; ++dy) {
+#pragma unroll
+    for (int dx = 0; dx < 5; ++dx) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float av = patch[((py + dy) * 20 + px + dx) * 3 + c];
+        const float4* wr = reinterpret_cast<const float4*>(wsm + ((dy * 5 + dx) * 3 + c) * 64);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 b = wr[j];
+          acc[4 * j + 0] = fmaf(av, b.x, acc[4 * j + 0]);
+          acc[4 * j + 1] = fmaf(av, b.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(av, b.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(av, b.w, acc[4 * j + 3]);
+        }
+      }
+    }
+  }
+  const int gy = y0 + py, gx = x0 + px;
+  if (gy < H && gx < W) {
+    const long long pix = ((long long)img * H + gy) * W + gx;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 8) {
+      __align__(16) __half oh[8];
+      __align__(16) __half ol[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = lrelu(acc[c0 + j] + bias[c0 + j]);
+        if (NSPLIT == 2)
+          split_half(v, oh[j], ol[j]);
+        else
+          oh[j] = __float2half_rn(v);
+      }
+      *reinterpret_cast<uint4*>(out_hi + pix * 64 + c0) = *reinterpret_cast<const uint4*>(oh);
+      if (NSPLIT == 2) *reinterpret_cast<uint4*>(out_lo + pix * 64 + c0) = *reinterpret_cast<const uint4*>(ol);
+    }
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------
+namespace {
+
+int g_num_sms = 0;
+int g_bo_mode = -1;
+
+int base_offset_mode() {
+  if (g_bo_mode < 0) {
+    const char* e = getenv("PFNL_TC_BASE_OFFSET");
+    g_bo_mode = e ? atoi(e) : kTcBaseOffsetMode;
+  }
+  return g_bo_mode;
+}
+
+template <int KS, int NSRC, int NSPLIT, int NOUT>
+int launch_tc(const void* src_hi, const void* src_lo, int src_images, const __half* wimg, TcConvParams p,
+              int out_images, cudaStream_t s) {
+  using C = TcCfg<KS, NSRC, NSPLIT, NOUT>;
+  CUtensorMap tmh, tml;
+  int r = make_act_tmap(&tmh, src_hi, src_images, p.H, p.W, C::BOX_W, C::BOX_H);
+  if (r == 0) r = make_act_tmap(&tml, NSPLIT == 2 ? src_lo : src_hi, src_images, p.H, p.W, C::BOX_W, C::BOX_H);
+  if (r != 0) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for images=%d H=%d W=%d", r, src_images, p.H, p.W);
+    return PFNL_ERR_CUDA;
+  }
+  p.tiles_x = ceil_div(p.W, 8);
+  p.tiles_y = ceil_div(p.H, 16);
+  p.n_tiles = out_images * p.tiles_x * p.tiles_y;
+  p.base_offset_mode = base_offset_mode();
+  if (p.n_tiles <= 0) return PFNL_OK;
+  const int grid = p.n_tiles < g_num_sms ? p.n_tiles : g_num_sms;
+  conv_tc_kernel<KS, NSRC, NSPLIT, NOUT><<<grid, 192, C::SMEM_BYTES, s>>>(tmh, tml, wimg, p);
+  PFNL_LAUNCH_CHECK();
+  return PFNL_OK;
+}
+
+template <int KS, int NSRC, int NSPLIT, int NOUT>
+int set_attr() {
+  PFNL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KS, NSRC, NSPLIT, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 TcCfg<KS, NSRC, NSPLIT, NOUT>::SMEM_BYTES));
+  return PFNL_OK;
+}
+
+size_t plane_bytes(int images, int H, int W) { return (size_t)images * H * W * 64 * sizeof(__half); }
+
+int pack_weights(const float* hwio, int taps, int cin_total, int ci_off, int cout, int nrows, int nsplit, void** out,
+                 std::vector<void*>& allocs) {
+  void* d = nullptr;
+  PFNL_CUDA(cudaMalloc(&d, (size_t)nsplit * taps * nrows * 128));
+  allocs.push_back(d);
+  const int total = taps * nrows * 64;
+  pack_tc_weights_kernel<<<ceil_div(total, 256), 256>>>(hwio, taps, cin_total, ci_off, cout, nrows, nsplit,
+                                                       (__half*)d, (size_t)taps * nrows * 128);
+  PFNL_LAUNCH_CHECK();
+  *out = d;
+  return PFNL_OK;
+}
+
+}  // namespace
+
+void tc_carve(TcWorkspace& w, int precision, int N, int H, int W, const std::function<char*(size_t)>& take) {
+  const int nsplit = precision == PFNL_PREC_TC_FP16X3 ? 2 : 1;
+  for (int pl = 0; pl < 2; ++pl) {
+    w.actA[pl] = w.actB[pl] = w.base[pl] = nullptr;
+  }
+  for (int pl = 0; pl < nsplit; ++pl) {
+    w.actA[pl] = take(plane_bytes(N * kFrames, H, W));
+    w.actB[pl] = take(plane_bytes(N * kFrames, H, W));
+    w.base[pl] = take(plane_bytes(N, H, W));
+  }
+  w.pbase = (float*)take((size_t)N * H * W * 64 * sizeof(float));
+  w.nl_x16 = nullptr;
+  w.nl_priv = nullptr;
+}
+
+int tc_init(TcWeights& tw, int precision, const TcRawWeights& raw, std::vector<void*>& allocs) {
+  if (!get_encode_tiled()) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return PFNL_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  int dev = 0;
+  PFNL_CUDA(cudaGetDevice(&dev));
+  PFNL_CUDA(cudaGetDeviceProperties(&prop, dev));
+  g_num_sms = prop.multiProcessorCount;
+  tw.precision = precision;
+  tw.nsplit = precision == PFNL_PREC_TC_FP16X3 ? 2 : 1;
+  tw.raw = raw;
+  int rc;
+  if ((rc = set_attr<3, 1, 1, 64>())) return rc;
+  if ((rc = set_attr<3, 1, 2, 64>())) return rc;
+  if ((rc = set_attr<1, 7, 1, 64>())) return rc;
+  if ((rc = set_attr<1, 7, 2, 64>())) return rc;
+  if ((rc = set_attr<3, 1, 1, 48>())) return rc;
+  if ((rc = set_attr<3, 1, 2, 48>())) return rc;
+  const int ns = tw.nsplit;
+  for (int i = 0; i < PFNL_NUM_BLOCK; ++i) {
+    if ((rc = pack_weights(raw.conv1_w[i], 9, 64, 0, 64, 64, ns, &tw.conv1[i], allocs))) return rc;
+    // conv10 [1,1,448,64]: "tap" t = frame slice t (input channels t*64..t*64+63)
+    void* d = nullptr;
+    PFNL_CUDA(cudaMalloc(&d, (size_t)ns * 7 * 64 * 128));
+    allocs.push_back(d);
+    tw.conv10[i] = d;
+    for (int t = 0; t < 7; ++t) {
+      // slice t -> [plane 0][t], its lo part -> [plane 1][t]
+      pack_tc_weights_kernel<<<16, 256>>>(raw.conv10_w[i], 1, 448, t * 64, 64, 64, ns,
+                                          (__half*)((uint8_t*)d + (size_t)t * 8192), (size_t)7 * 8192);
+      PFNL_LAUNCH_CHECK();
+    }
+    if ((rc = pack_weights(raw.conv2_w[i], 9, 128, 0, 64, 64, ns, &tw.conv2b[i], allocs))) return rc;
+    if ((rc = pack_weights(raw.conv2_w[i], 9, 128, 64, 64, 64, ns, &tw.conv2f[i], allocs))) return rc;
+  }
+  // convmerge1 [3,3,448,48]: one weight image per frame slice t (launched 7 times, accumulating)
+  {
+    void* d = nullptr;
+    const size_t per = (size_t)ns * 9 * 48 * 128;
+    PFNL_CUDA(cudaMalloc(&d, per * 7));
+    allocs.push_back(d);
+    tw.merge1 = d;
+    for (int t = 0; t < 7; ++t) {
+      pack_tc_weights_kernel<<<ceil_div(9 * 48 * 64, 256), 256>>>(raw.merge1_w, 9, 448, t * 64, 48, 48, ns,
+                                                                  (__half*)((uint8_t*)d + per * t),
+                                                                  (size_t)9 * 48 * 128);
+      PFNL_LAUNCH_CHECK();
+    }
+  }
+  PFNL_CUDA(cudaDeviceSynchronize());
+  return PFNL_OK;
+}
+
+void tc_destroy(TcWeights&) {}
+
+namespace {
+
+// One PFRB (model/pfnl.py:66-71) on fp16 planes, in place on actA.
+template <int NSPLIT>
+int pfrb_tc(const TcWeights& tw, TcWorkspace& w, int i, int N, int H, int W, cudaStream_t s, long long* launches,
+            Profiler* prof) {
+  TcConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.H = H;
+  p.W = W;
+  int rc;
+  // inp1[t] = conv1_i(inp0[t])                                   pfnl.py:66
+  p.img_mul = 1;
+  p.img_add = 0;
+  p.epi = kEpiActPlanes;
+  p.bias = tw.raw.conv1_b[i];
+  p.out_hi = (__half*)w.actB[0];
+  p.out_lo = (__half*)w.actB[1];
+  if (prof) prof->begin(kProfConv1, s);
+  rc = launch_tc<3, 1, NSPLIT, 64>(w.actA[0], w.actA[1], N * kFrames, (const __half*)tw.conv1[i], p, N * kFrames, s);
+  if (prof) prof->end(s);
+  if (rc) return rc;
+  // base = conv10_i(concat_t inp1[t])                            pfnl.py:67-68  (7 K-slices, no concat copy)
+  p.img_mul = kFrames;
+  p.bias = tw.raw.conv10_b[i];
+  p.out_hi = (__half*)w.base[0];
+  p.out_lo = (__half*)w.base[1];
+  if (prof) prof->begin(kProfConv10, s);
+  rc = launch_tc<1, 7, NSPLIT, 64>(w.actB[0], w.actB[1], N * kFrames, (const __half*)tw.conv10[i], p, N, s);
+  if (prof) prof->end(s);
+  if (rc) return rc;
+  // conv2_i(concat[base, inp1[t]]) = conv(base; W2[:,:,0:64]) + conv(inp1[t]; W2[:,:,64:128]):
+  // the base half is identical for the 7 frames -> computed once (fp32 partial sums)
+  p.img_mul = 1;
+  p.epi = kEpiPartialF32;
+  p.accumulate = 0;
+  p.bias = nullptr;
+  p.out_f32 = w.pbase;
+  if (prof) prof->begin(kProfOther, s);
+  rc = launch_tc<3, 1, NSPLIT, 64>(w.base[0], w.base[1], N, (const __half*)tw.conv2b[i], p, N, s);
+  if (prof) prof->end(s);
+  if (rc) return rc;
+  // inp0[t] += leaky_relu(partial + conv(inp1[t]) + bias)         pfnl.py:70-71
+  p.epi = kEpiResPlanes;
+  p.bias = tw.raw.conv2_b[i];
+  p.pbase = w.pbase;
+  p.pb_div = kFrames;
+  p.res_hi = (const __half*)w.actA[0];
+  p.res_lo = (const __half*)w.actA[1];
+  p.out_hi = (__half*)w.actA[0];
+  p.out_lo = (__half*)w.actA[1];
+  if (prof) prof->begin(kProfConv2, s);
+  rc = launch_tc<3, 1, NSPLIT, 64>(w.actB[0], w.actB[1], N * kFrames, (const __half*)tw.conv2f[i], p, N * kFrames, s);
+  if (prof) prof->end(s);
+  if (rc) return rc;
+  *launches += 4;
+  return PFNL_OK;
+}
+
+template <int NSPLIT>
+int trunk_tc(const TcWeights& tw, TcWorkspace& w, const float* inp21, int N, int H, int W, float* merge,
+             cudaStream_t s, long long* launches, Profiler* prof) {
+  int rc;
+  dim3 grid(ceil_div(W, 16) * ceil_div(H, 16), N * kFrames);
+  if (prof) prof->begin(kProfConv0, s);
+  conv0_planes_kernel<NSPLIT><<<grid, 256, 0, s>>>(inp21, H, W, tw.raw.conv0_w, tw.raw.conv0_b, (__half*)w.actA[0],
+                                                   (__half*)w.actA[1]);
+  if (prof) prof->end(s);
+  PFNL_LAUNCH_CHECK();
+  *launches += 1;
+  for (int i = 0; i < PFNL_NUM_BLOCK; ++i)
+    if ((rc = pfrb_tc<NSPLIT>(tw, w, i, N, H, W, s, launches, prof))) return rc;
+  // merge = convmerge1(concat_t inp0[t])                          pfnl.py:73-74: 7 accumulating launches
+  TcConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.H = H;
+  p.W = W;
+  p.img_mul = kFrames;
+  p.out_f32 = merge;
+  const size_t per = (size_t)NSPLIT * 9 * 48 * 128;
+  if (prof) prof->begin(kProfMerge1, s);
+  for (int t = 0; t < kFrames; ++t) {
+    p.img_add = t;
+    p.epi = t == kFrames - 1 ? kEpiFinalF32 : kEpiPartialF32;
+    p.accumulate = t > 0;
+    p.bias = t == kFrames - 1 ? tw.raw.merge1_b : nullptr;
+    rc = launch_tc<3, 1, NSPLIT, 48>(w.actA[0], w.actA[1], N * kFrames,
+                                     (const __half*)((const uint8_t*)tw.merge1 + per * t), p, N, s);
+    if (rc) return rc;
+  }
+  if (prof) prof->end(s);
+  *launches += kFrames;
+  return PFNL_OK;
+}
+
+}  // namespace
+
+int tc_trunk(const TcWeights& tw, TcWorkspace& w, int precision, const float* inp21, int N, int H, int W,
+             float* merge, cudaStream_t s, long long* launches, Profiler* prof) {
+  if (precision == PFNL_PREC_TC_FP16X3) return trunk_tc<2>(tw, w, inp21, N, H, W, merge, s, launches, prof);
+  return trunk_tc<1>(tw, w, inp21, N, H, W, merge, s, launches, prof);
+}
+
+int tc_pfrb_fp32io(const TcWeights& tw, TcWorkspace& w, int precision, int blk, const float* frames, int N, int H,
+                   int W, float* frames_out, cudaStream_t s, long long* launches) {
+  const int ns = precision == PFNL_PREC_TC_FP16X3 ? 2 : 1;
+  const long long n = (long long)N * kFrames * H * W * 64;
+  f32_to_planes_kernel<<<148 * 8, 256, 0, s>>>(frames, n, ns, (__half*)w.actA[0], (__half*)w.actA[1]);
+  PFNL_LAUNCH_CHECK();
+  int rc = ns == 2 ? pfrb_tc<2>(tw, w, blk, N, H, W, s, launches, nullptr)
+                   : pfrb_tc<1>(tw, w, blk, N, H, W, s, launches, nullptr);
+  if (rc) return rc;
+  planes_to_f32_kernel<<<148 * 8, 256, 0, s>>>((const __half*)w.actA[0], (const __half*)w.actA[1], n, ns, frames_out);
+  PFNL_LAUNCH_CHECK();
+  *launches += 2;
+  return PFNL_OK;
+}
+
+}  // namespace pfnl

@@ -11,6 +11,13 @@
 
 namespace pfnl {
 
+// Shared-memory halo patch of the 3x3 tensor-core conv: row pitch in pixels (TMA box width) and
+// the UMMA descriptor base-offset convention.  Settled by probes/umma_probe.cu on a B200 (see
+// DESIGN.md): the swizzle is a function of the absolute smem address, so a pitch of 10 pixels
+// (no padding) with base_offset = 0 is exact; base_offset = (start>>7)&7 is WRONG on B200.
+constexpr int kTcPatchW3 = 10;
+constexpr int kTcBaseOffsetMode = 0;
+
 struct TcRawWeights {  // fp32 HWIO device pointers owned by the handle
   const float *nl_g_w, *nl_g_b, *nl_w_w, *nl_w_b;
   const float *conv0_w, *conv0_b;
@@ -60,6 +67,7 @@ void tc_destroy(TcWeights& tw);
 // conv0 .. convmerge1 (model/pfnl.py:61-74): inp21 [N,H,W,21] fp32 -> merge [N,H,W,48] fp32
 int tc_trunk(const TcWeights& tw, TcWorkspace& w, int precision, const float* inp21, int N, int H, int W,
              float* merge, cudaStream_t s, long long* launches, Profiler* prof);
+bool tc_has_nonlocal();
 // tokens [N,L,84] (+ lr for the residual) -> inp21 [N,H,W,21]   (model/pfnl.py:58-60)
 int tc_nonlocal(const TcWeights& tw, TcWorkspace& w, const float* tokens, const float* lr, int N, int H, int W,
                 float* inp21, cudaStream_t s, long long* launches, Profiler* prof);
