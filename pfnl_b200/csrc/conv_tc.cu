@@ -5,20 +5,26 @@
 // 128-byte row = one 128B-swizzle row).  PFNL_PREC_TC_FP16 keeps one plane per tensor;
 // PFNL_PREC_TC_FP16X3 keeps two (hi = fp16(v), lo = fp16((v-hi)*2048)) and runs three MMAs per
 // k-step (hi*hi into D0; hi*lo' + lo'*hi into D1; result D0 + D1/2048), which carries ~22
-// mantissa bits through the fp16 tensor pipe.
+// mantissa bits through the fp16 tensor pipe.  TMEM accumulation truncates (measured by
+// probes/umma_probe.cu), so in the x3 mode D0 is split into NCH accumulation chains (one per
+// kernel row) that are summed round-to-nearest in the epilogue: fewer truncating adds per chain.
 //
 // Implicit GEMM: M = 128 output pixels (a 16-row x 8-column spatial tile of one image),
 // N = 64 (48 for convmerge1) output channels, K = taps x 64 input channels.  Per tile ONE TMA
-// box {64 ch, BOX_W px, 18 rows} (out-of-bounds zero fill == 'same' zero padding) lands a halo
+// box {64 ch, 10 px, 18 rows} (out-of-bounds zero fill == 'same' zero padding) lands a halo
 // patch in smem; the A operand of tap (dy,dx) is the same patch addressed through a UMMA
-// descriptor whose start is shifted by (dy*BOX_W+dx) 128-byte rows and whose 8-row-group stride
-// (SBO) is BOX_W*128 - so each input byte is fetched from L2 once per tile, not 9 times.
+// descriptor whose start is shifted by (dy*10+dx) 128-byte rows and whose 8-row-group stride
+// (SBO) is 10*128 - so each input byte is fetched from L2 once per tile, not 9 times.  (The
+// 128B swizzle is a function of the absolute smem address on B200, so shifted windows need no
+// padding and base_offset = 0; probes/umma_probe.cu.)
 // Weights ([taps][N][64] fp16, pre-swizzled) stay resident in smem for the CTA's lifetime.
 //
 // Warp roles (192 threads, 1 CTA / SM, persistent over tiles): warp 0 = TMA producer, warp 1 =
-// MMA issuer (one elected lane), warps 2-5 = epilogue (tcgen05.ld -> bias / leaky_relu / partial
-// sums / residual -> fp16 planes or fp32).  TMEM accumulators are double buffered so the
-// epilogue of tile i overlaps the MMAs of tile i+1.
+// MMA issuer (converged warp, one elected lane issues), warps 2-5 = epilogue (tcgen05.ld -> bias /
+// leaky_relu / partial sums / residual -> fp16 planes or fp32).  TMEM accumulators are double
+// buffered so the epilogue of tile i overlaps the MMAs of tile i+1.  Launched with programmatic
+// dependent launch: the prologue (barriers, TMEM alloc, weight load) overlaps the previous
+// kernel's tail; griddepcontrol.wait guards every access to activations.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -44,7 +50,6 @@ struct TcConvParams {
   int epi;
   int accumulate;        // kEpiPartialF32: add the previous content of out_f32
   int pb_div;            // pbase image index = out_img / pb_div
-  int base_offset_mode;  // UMMA descriptor base-offset field: 0 -> 0, 1 -> (start>>7)&7
   const float* bias;     // [NOUT]
   const float* pbase;    // fp32 [out_img/pb_div][H][W][64]
   __half* out_hi;
@@ -54,7 +59,7 @@ struct TcConvParams {
   float* out_f32;        // [out_images][H][W][NOUT]
 };
 
-template <int KS, int NSRC, int NSPLIT, int NOUT>
+template <int KS, int NSRC, int NSPLIT, int NOUT, int NCH>
 struct TcCfg {
   static constexpr int TAPS = KS * KS;
   static constexpr int NTAPS = NSRC * TAPS;
@@ -71,8 +76,12 @@ struct TcCfg {
   static constexpr int NL = NSPLIT == 1 ? 0 : (TOTAL_SLOTS / 2 > 3 ? 3 : TOTAL_SLOTS / 2);
   static constexpr int NH = (TOTAL_SLOTS - NL) > 4 ? 4 : (TOTAL_SLOTS - NL);
   static constexpr int SMEM_BYTES = 1024 + CTRL_BYTES + W_BYTES + (NH + NL) * SLOT_BYTES;
-  static constexpr int TMEM_BUF_COLS = NSPLIT * 64;
-  static constexpr int TMEM_COLS = 2 * TMEM_BUF_COLS;  // 128 or 256 (power of two)
+  // TMEM per accumulator buffer: NCH chains of D0 (+ D1 in the split mode), 64 columns each
+  static constexpr int D1_COL = NCH * 64;
+  static constexpr int TMEM_BUF_COLS = (NCH + (NSPLIT == 2 ? 1 : 0)) * 64;
+  static constexpr int TMEM_NEED = 2 * TMEM_BUF_COLS;
+  static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
+  static_assert(TMEM_NEED <= 512, "TMEM overflow");
   static_assert(NH >= 1 && (NSPLIT == 1 || NL >= 1), "shared memory budget too small");
   static_assert(SMEM_BYTES <= SMEM_MAX, "shared memory overflow");
 };
@@ -91,11 +100,23 @@ __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
   lo = __float2half_rn((v - __half2float(hi)) * 2048.f);
 }
 
-template <int KS, int NSRC, int NSPLIT, int NOUT>
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <int KS, int NSRC, int NSPLIT, int NOUT, int NCH>
 __global__ void __launch_bounds__(192, 1)
     conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                    const __half* __restrict__ wimg, const TcConvParams p) {
-  using C = TcCfg<KS, NSRC, NSPLIT, NOUT>;
+  using C = TcCfg<KS, NSRC, NSPLIT, NOUT, NCH>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* wsm = smem;                                  // [NSPLIT][NTAPS][WT_BYTES]
@@ -105,6 +126,8 @@ __global__ void __launch_bounds__(192, 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int PAD = (KS - 1) / 2;
 
+  // ---- prologue: touches only weights / bias (never written by any kernel), overlaps the previous
+  //      kernel's tail under programmatic dependent launch
   if (tid == 0) {
     mbar_init(&ctl->wfull, 1);
     for (int i = 0; i < 4; ++i) {
@@ -121,6 +144,11 @@ __global__ void __launch_bounds__(192, 1)
     fence_proxy_async();
     tma_prefetch_desc(&tm_hi);
     if (NSPLIT == 2) tma_prefetch_desc(&tm_lo);
+    mbar_arrive_expect_tx(&ctl->wfull, C::W_BYTES);
+    for (int off = 0; off < C::W_BYTES; off += 32768) {
+      const int n = (C::W_BYTES - off) < 32768 ? (C::W_BYTES - off) : 32768;
+      bulk_load(wsm + off, reinterpret_cast<const uint8_t*>(wimg) + off, n, &ctl->wfull);
+    }
   }
   if (tid < 64) ctl->bias[tid] = (p.bias != nullptr && tid < NOUT) ? p.bias[tid] : 0.f;
   if (warp == 1) {
@@ -131,15 +159,12 @@ __global__ void __launch_bounds__(192, 1)
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = ctl->tmem_base;
+  pdl_launch_dependents();  // let the next kernel's CTAs start their prologue as SMs free up
+  pdl_wait();               // activations written by the previous kernel are visible after this
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_arrive_expect_tx(&ctl->wfull, C::W_BYTES);
-      for (int off = 0; off < C::W_BYTES; off += 32768) {
-        const int n = (C::W_BYTES - off) < 32768 ? (C::W_BYTES - off) : 32768;
-        bulk_load(wsm + off, reinterpret_cast<const uint8_t*>(wimg) + off, n, &ctl->wfull);
-      }
       int sh = 0, ph = 0, sl = 0, pl = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int tx = tile % p.tiles_x;
@@ -170,74 +195,85 @@ __global__ void __launch_bounds__(192, 1)
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(128, NOUT);
-      constexpr uint32_t SBO_A = C::BOX_W * 128;
-      constexpr uint32_t SBO_B = 1024;
-      const uint32_t w_hi = smem_u32(wsm);
-      const uint32_t w_lo = w_hi + C::NTAPS * C::WT_BYTES;
-      mbar_wait(&ctl->wfull, 0);
+    // The whole warp walks the loop converged (waits are warp-uniform); one elected lane issues.
+    // Descriptors are advanced by adding compile-time constants to a per-slot base descriptor:
+    // ~3 instructions per tcgen05.mma instead of rebuilding two descriptors each time.
+    constexpr uint32_t idesc = make_idesc_f16(128, NOUT);
+    constexpr uint32_t SBO_A = C::BOX_W * 128;
+    const uint64_t wd_hi = make_sdesc_sw128(smem_u32(wsm), 1024, 0);
+    const uint64_t wd_lo = make_sdesc_sw128(smem_u32(wsm) + C::NTAPS * C::WT_BYTES, 1024, 0);
+    mbar_wait(&ctl->wfull, 0);
+    fence_after_sync();
+    int sh = 0, ph = 0, sl = 0, pl = 0, it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&ctl->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
       fence_after_sync();
-      int sh = 0, ph = 0, sl = 0, pl = 0, it = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        mbar_wait(&ctl->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
-        fence_after_sync();
-        const uint32_t d0 = tmem + buf * C::TMEM_BUF_COLS;
-        const uint32_t d1 = d0 + 64;
-        uint32_t acc0 = 0, acc1 = 0;
-        for (int s = 0; s < NSRC; ++s) {
-          if (NSPLIT == 2) {
-            // lo-plane pass first: its patch slot is released early and refilled under the hi pass
-            mbar_wait(&ctl->full_lo[sl], pl);
-            fence_after_sync();
-            const uint32_t a_base = smem_u32(ring_lo + sl * C::SLOT_BYTES);
+      const uint32_t dbase = tmem + buf * C::TMEM_BUF_COLS;
+      const uint32_t d1 = dbase + C::D1_COL;
+      uint32_t acc1 = 0;
+      uint32_t accmask = 0;  // bit c set once chain c has been written in this tile
+      for (int s = 0; s < NSRC; ++s) {
+        const uint64_t wsd_hi = wd_hi + (uint64_t)((s * C::TAPS * C::WT_BYTES) >> 4);
+        const uint64_t wsd_lo = wd_lo + (uint64_t)((s * C::TAPS * C::WT_BYTES) >> 4);
+        if (NSPLIT == 2) {
+          // lo-plane pass first: its patch slot is released early and refilled under the hi pass
+          mbar_wait(&ctl->full_lo[sl], pl);
+          fence_after_sync();
+          const uint64_t ad = make_sdesc_sw128(smem_u32(ring_lo + sl * C::SLOT_BYTES), SBO_A, 0);
+          if (elect_one()) {
 #pragma unroll
             for (int t = 0; t < C::TAPS; ++t) {
-              const uint32_t shift = ((t / KS) * C::BOX_W + (t % KS)) * 128;
-              const uint32_t wt = w_hi + (s * C::TAPS + t) * C::WT_BYTES;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint32_t a = a_base + shift + k * 32;
-                const uint32_t bo = p.base_offset_mode ? ((a >> 7) & 7) : 0;
-                mma_f16(d1, make_sdesc_sw128(a, SBO_A, bo), make_sdesc_sw128(wt + k * 32, SBO_B, 0), idesc, acc1);
+                const uint32_t aoff = (((t / KS) * C::BOX_W + (t % KS)) * 128 + k * 32) >> 4;
+                const uint32_t boff = (t * C::WT_BYTES + k * 32) >> 4;
+                mma_f16(d1, ad + aoff, wsd_hi + boff, idesc, acc1);
                 acc1 = 1;
               }
             }
             mma_commit(&ctl->empty_lo[sl]);
-            if (++sl == C::NL) {
-              sl = 0;
-              pl ^= 1;
-            }
           }
-          mbar_wait(&ctl->full_hi[sh], ph);
-          fence_after_sync();
-          const uint32_t a_base = smem_u32(ring_hi + sh * C::SLOT_BYTES);
+          __syncwarp();
+          acc1 = 1;
+          if (++sl == C::NL) {
+            sl = 0;
+            pl ^= 1;
+          }
+        }
+        mbar_wait(&ctl->full_hi[sh], ph);
+        fence_after_sync();
+        const uint64_t ad = make_sdesc_sw128(smem_u32(ring_hi + sh * C::SLOT_BYTES), SBO_A, 0);
+        if (elect_one()) {
+          uint32_t am = accmask;
+          uint32_t a1 = acc1;
 #pragma unroll
           for (int t = 0; t < C::TAPS; ++t) {
-            const uint32_t shift = ((t / KS) * C::BOX_W + (t % KS)) * 128;
-            const uint32_t wt = w_hi + (s * C::TAPS + t) * C::WT_BYTES;
-            const uint32_t wl = w_lo + (s * C::TAPS + t) * C::WT_BYTES;
+            const int ch = (KS == 3 ? (t / KS) : s) % NCH;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint32_t a = a_base + shift + k * 32;
-              const uint32_t bo = p.base_offset_mode ? ((a >> 7) & 7) : 0;
-              const uint64_t ad = make_sdesc_sw128(a, SBO_A, bo);
-              mma_f16(d0, ad, make_sdesc_sw128(wt + k * 32, SBO_B, 0), idesc, acc0);
-              acc0 = 1;
+              const uint32_t aoff = (((t / KS) * C::BOX_W + (t % KS)) * 128 + k * 32) >> 4;
+              const uint32_t boff = (t * C::WT_BYTES + k * 32) >> 4;
+              mma_f16(dbase + ch * 64, ad + aoff, wsd_hi + boff, idesc, (am >> ch) & 1u);
+              am |= 1u << ch;
               if (NSPLIT == 2) {
-                mma_f16(d1, ad, make_sdesc_sw128(wl + k * 32, SBO_B, 0), idesc, acc1);
-                acc1 = 1;
+                mma_f16(d1, ad + aoff, wsd_lo + boff, idesc, a1);
+                a1 = 1;
               }
             }
           }
           mma_commit(&ctl->empty_hi[sh]);
-          if (++sh == C::NH) {
-            sh = 0;
-            ph ^= 1;
-          }
+          if (s == NSRC - 1) mma_commit(&ctl->tmem_full[buf]);  // same thread that issued the MMAs
         }
-        mma_commit(&ctl->tmem_full[buf]);
+        __syncwarp();
+        // every lane tracks the same chain state (the elected lane may change between calls)
+#pragma unroll
+        for (int t = 0; t < C::TAPS; ++t) accmask |= 1u << ((KS == 3 ? (t / KS) : s) % NCH);
+        acc1 = 1;
+        if (++sh == C::NH) {
+          sh = 0;
+          ph ^= 1;
+        }
       }
     }
   } else {
@@ -260,14 +296,18 @@ __global__ void __launch_bounds__(192, 1)
       const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + buf * C::TMEM_BUF_COLS;
 #pragma unroll
       for (int c0 = 0; c0 < NOUT; c0 += 16) {
-        uint32_t r0[16], r1[16];
+        uint32_t r0[16], r1[16], r2[16], r3[16];
         tmem_ld_32x32b_x16(t0 + c0, r0);
-        if (NSPLIT == 2) tmem_ld_32x32b_x16(t0 + 64 + c0, r1);
+        if (NCH >= 2) tmem_ld_32x32b_x16(t0 + 64 + c0, r2);
+        if (NCH >= 3) tmem_ld_32x32b_x16(t0 + 128 + c0, r3);
+        if (NSPLIT == 2) tmem_ld_32x32b_x16(t0 + C::D1_COL + c0, r1);
         tmem_ld_wait();
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           v[j] = __uint_as_float(r0[j]);
+          if (NCH >= 2) v[j] += __uint_as_float(r2[j]);
+          if (NCH >= 3) v[j] += __uint_as_float(r3[j]);
           if (NSPLIT == 2) v[j] = fmaf(__uint_as_float(r1[j]), 1.f / 2048.f, v[j]);
         }
         if (inb) {
@@ -291,20 +331,22 @@ __global__ void __launch_bounds__(192, 1)
               const uint4 a0 = rh[0], a1 = rh[1];
               const __half* hh0 = reinterpret_cast<const __half*>(&a0);
               const __half* hh1 = reinterpret_cast<const __half*>(&a1);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                v[j] += __half2float(hh0[j]);
-                v[8 + j] += __half2float(hh1[j]);
-              }
               if (NSPLIT == 2) {
+                // residual = hi + lo/2048 (exactly representable in fp32), then one rounded add
                 const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + pix * 64 + c0);
                 const uint4 b0 = rl[0], b1 = rl[1];
                 const __half* hl0 = reinterpret_cast<const __half*>(&b0);
                 const __half* hl1 = reinterpret_cast<const __half*>(&b1);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  v[j] = fmaf(__half2float(hl0[j]), 1.f / 2048.f, v[j]);
-                  v[8 + j] = fmaf(__half2float(hl1[j]), 1.f / 2048.f, v[8 + j]);
+                  v[j] += fmaf(__half2float(hl0[j]), 1.f / 2048.f, __half2float(hh0[j]));
+                  v[8 + j] += fmaf(__half2float(hl1[j]), 1.f / 2048.f, __half2float(hh1[j]));
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  v[j] += __half2float(hh0[j]);
+                  v[8 + j] += __half2float(hh1[j]);
                 }
               }
             }
@@ -476,20 +518,21 @@ __global__ void __launch_bounds__(256) conv0_planes_kernel(const float* __restri
 namespace {
 
 int g_num_sms = 0;
-int g_bo_mode = -1;
+int g_chains = -1;
 
-int base_offset_mode() {
-  if (g_bo_mode < 0) {
-    const char* e = getenv("PFNL_TC_BASE_OFFSET");
-    g_bo_mode = e ? atoi(e) : kTcBaseOffsetMode;
+// x3 mode: number of D0 accumulation chains of the 3x3 kernels (1 or 3; PFNL_TC_CHAINS overrides)
+int x3_chains() {
+  if (g_chains < 0) {
+    const char* e = getenv("PFNL_TC_CHAINS");
+    g_chains = (e && atoi(e) == 1) ? 1 : 3;
   }
-  return g_bo_mode;
+  return g_chains;
 }
 
-template <int KS, int NSRC, int NSPLIT, int NOUT>
-int launch_tc(const void* src_hi, const void* src_lo, int src_images, const __half* wimg, TcConvParams p,
+template <int KS, int NSRC, int NSPLIT, int NOUT, int NCH>
+int launch_tc_impl(const void* src_hi, const void* src_lo, int src_images, const __half* wimg, TcConvParams p,
               int out_images, cudaStream_t s) {
-  using C = TcCfg<KS, NSRC, NSPLIT, NOUT>;
+  using C = TcCfg<KS, NSRC, NSPLIT, NOUT, NCH>;
   CUtensorMap tmh, tml;
   int r = make_act_tmap(&tmh, src_hi, src_images, p.H, p.W, C::BOX_W, C::BOX_H);
   if (r == 0) r = make_act_tmap(&tml, NSPLIT == 2 ? src_lo : src_hi, src_images, p.H, p.W, C::BOX_W, C::BOX_H);
@@ -500,18 +543,37 @@ int launch_tc(const void* src_hi, const void* src_lo, int src_images, const __ha
   p.tiles_x = ceil_div(p.W, 8);
   p.tiles_y = ceil_div(p.H, 16);
   p.n_tiles = out_images * p.tiles_x * p.tiles_y;
-  p.base_offset_mode = base_offset_mode();
   if (p.n_tiles <= 0) return PFNL_OK;
   const int grid = p.n_tiles < g_num_sms ? p.n_tiles : g_num_sms;
-  conv_tc_kernel<KS, NSRC, NSPLIT, NOUT><<<grid, 192, C::SMEM_BYTES, s>>>(tmh, tml, wimg, p);
-  PFNL_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PFNL_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<KS, NSRC, NSPLIT, NOUT, NCH>, tmh, tml, wimg, p));
   return PFNL_OK;
 }
 
 template <int KS, int NSRC, int NSPLIT, int NOUT>
+int launch_tc(const void* src_hi, const void* src_lo, int src_images, const __half* wimg, TcConvParams p,
+              int out_images, cudaStream_t s) {
+  if (KS == 3 && NSPLIT == 2 && x3_chains() == 3)
+    return launch_tc_impl<KS, NSRC, NSPLIT, NOUT, (KS == 3 && NSPLIT == 2) ? 3 : 1>(src_hi, src_lo, src_images, wimg, p,
+                                                                                  out_images, s);
+  return launch_tc_impl<KS, NSRC, NSPLIT, NOUT, 1>(src_hi, src_lo, src_images, wimg, p, out_images, s);
+}
+
+template <int KS, int NSRC, int NSPLIT, int NOUT, int NCH>
 int set_attr() {
-  PFNL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KS, NSRC, NSPLIT, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 TcCfg<KS, NSRC, NSPLIT, NOUT>::SMEM_BYTES));
+  PFNL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KS, NSRC, NSPLIT, NOUT, NCH>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 TcCfg<KS, NSRC, NSPLIT, NOUT, NCH>::SMEM_BYTES));
   return PFNL_OK;
 }
 
@@ -545,6 +607,11 @@ void tc_carve(TcWorkspace& w, int precision, int N, int H, int W, const std::fun
   w.pbase = (float*)take((size_t)N * H * W * 64 * sizeof(float));
   w.nl_x16 = nullptr;
   w.nl_priv = nullptr;
+  if (precision == PFNL_PREC_TC_FP16 && tc_has_nonlocal()) {
+    const int L = (H / 2) * (W / 2);
+    w.nl_x16 = take(tc_nl_workspace_bytes(N, L));
+    w.nl_priv = take((size_t)N * L * kNL * sizeof(float));  // Y = softmax(S) * G, fp32 [N,L,84]
+  }
 }
 
 int tc_init(TcWeights& tw, int precision, const TcRawWeights& raw, std::vector<void*>& allocs) {
@@ -561,12 +628,15 @@ int tc_init(TcWeights& tw, int precision, const TcRawWeights& raw, std::vector<v
   tw.nsplit = precision == PFNL_PREC_TC_FP16X3 ? 2 : 1;
   tw.raw = raw;
   int rc;
-  if ((rc = set_attr<3, 1, 1, 64>())) return rc;
-  if ((rc = set_attr<3, 1, 2, 64>())) return rc;
-  if ((rc = set_attr<1, 7, 1, 64>())) return rc;
-  if ((rc = set_attr<1, 7, 2, 64>())) return rc;
-  if ((rc = set_attr<3, 1, 1, 48>())) return rc;
-  if ((rc = set_attr<3, 1, 2, 48>())) return rc;
+  if ((rc = set_attr<3, 1, 1, 64, 1>())) return rc;
+  if ((rc = set_attr<3, 1, 2, 64, 1>())) return rc;
+  if ((rc = set_attr<3, 1, 2, 64, 3>())) return rc;
+  if ((rc = set_attr<1, 7, 1, 64, 1>())) return rc;
+  if ((rc = set_attr<1, 7, 2, 64, 1>())) return rc;
+  if ((rc = set_attr<3, 1, 1, 48, 1>())) return rc;
+  if ((rc = set_attr<3, 1, 2, 48, 1>())) return rc;
+  if ((rc = set_attr<3, 1, 2, 48, 3>())) return rc;
+  if ((rc = tc_nl_init())) return rc;
   const int ns = tw.nsplit;
   for (int i = 0; i < PFNL_NUM_BLOCK; ++i) {
     if ((rc = pack_weights(raw.conv1_w[i], 9, 64, 0, 64, 64, ns, &tw.conv1[i], allocs))) return rc;

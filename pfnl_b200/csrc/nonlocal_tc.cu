@@ -1,20 +1,409 @@
-// tcgen05 non-local block (PFNL_PREC_TC_FP16) - under construction: until it lands the fp16
-// precision uses the fp32 FFMA non-local kernels (nonlocal_ffma.cu), never a CPU path.
+// Non-local block on tcgen05 tensor cores (PFNL_PREC_TC_FP16): NonLocalBlock nltype=1 'gaussian',
+// sub_sample=1 (utils.py:18-71) with theta = phi = X (utils.py:33-34,41-42).
+//
+//   nl_prep_kernel   X fp32 [N,L,84] -> X16 [N,Lp,128] fp16 (zero padded; the Q/K operand) and
+//                    G = X*Wg+bg (utils.py:26, fp32 FFMA) -> Gt16 [N,96,Lp] fp16 (V, stored
+//                    channel-major so that the PV B-operand is K-major)
+//   nl_tc_kernel     per (clip, 128-query tile): TMA -> smem, S = Q K^T (tcgen05, fp32 in TMEM),
+//                    online softmax (each of 128 threads owns one query row of S: row max / exp /
+//                    sum are thread-local, no shuffles), P (fp16) -> smem, O += P V (tcgen05),
+//                    running-max correction of the TMEM-resident O (tcgen05.ld/st), Y = O / l.
+//                    The L x L matrix (utils.py:53-58) is never materialised.
+//   then             Z = Y*Ww+bw, depth_to_space, + input  (nl_linear_scatter, nonlocal_ffma.cu)
+//
+// Shared memory / TMEM per CTA: Q 32 KB, 2 x (K 32 KB + V 24 KB) ring, P 32 KB; TMEM 2 x 128
+// columns of S (double buffered: S(j+1) is issued while softmax(j) runs) + 96 columns of O.
+#include <cuda_fp16.h>
+#include <math.h>
+
 #include "common.cuh"
+#include "kernels.h"
 #include "tc.h"
+#include "tc_ptx.cuh"
+#include "tc_tmap.h"
 
 namespace pfnl {
 
-bool tc_has_nonlocal() { return false; }
+using namespace tc;
 
-int tc_nonlocal(const TcWeights&, TcWorkspace&, const float*, const float*, int, int, int, float*, cudaStream_t,
-                long long*, Profiler*) {
-  set_error("tensor-core non-local kernel not built");
-  return PFNL_ERR_UNIMPLEMENTED;
+namespace {
+
+constexpr int kQT = 128;   // queries per CTA
+constexpr int kKT = 128;   // keys per tile
+constexpr int kCP = 128;   // padded channel count of X16 (84 -> 128: two 64-wide K blocks)
+constexpr int kVR = 96;    // padded channel count of Gt16 rows (84 -> 96, multiple of 16)
+
+struct NlCtrl {
+  uint64_t q_full;
+  uint64_t k_full[2], k_empty[2];
+  uint64_t v_full[2], v_empty[2];
+  uint64_t s_full[2], s_empty[2];
+  uint64_t p_ready, pv_done;
+  uint32_t tmem_base;
+};
+
+constexpr int kQBytes = 2 * kQT * 128;          // 32768
+constexpr int kKBytes = 2 * kKT * 128;          // 32768
+constexpr int kVBytes = 2 * kVR * 128;          // 24576
+constexpr int kPBytes = 2 * kQT * 128;          // 32768
+constexpr int kNlSmem = 1024 + kQBytes + 2 * (kKBytes + kVBytes) + kPBytes + 1024;
+
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
 }
-int tc_nonlocal_tokens(const TcWeights&, const float*, int, int, float*, cudaStream_t, long long*) {
-  set_error("tensor-core non-local kernel not built");
-  return PFNL_ERR_UNIMPLEMENTED;
+__device__ __forceinline__ bool elect_one_nl() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 2-D map over a row-major fp16 matrix [rows, cols]: box = (64 cols, box_rows), 128B swizzle.
+int make_mat_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_tiled();
+  if (!fn) return -1;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return (int)fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+__global__ void __launch_bounds__(192, 1)
+    nl_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g, int L, int Lp,
+                 float* __restrict__ Y) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* q_sm = smem;
+  uint8_t* k_sm = q_sm + kQBytes;            // [2][kKBytes]
+  uint8_t* v_sm = k_sm + 2 * kKBytes;        // [2][kVBytes]
+  uint8_t* p_sm = v_sm + 2 * kVBytes;
+  NlCtrl* ctl = reinterpret_cast<NlCtrl*>(p_sm + kPBytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.y, q0 = blockIdx.x * kQT;
+  const int ntiles = Lp / kKT;
+
+  if (tid == 0) {
+    mbar_init(&ctl->q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctl->k_full[i], 1);
+      mbar_init(&ctl->k_empty[i], 1);
+      mbar_init(&ctl->v_full[i], 1);
+      mbar_init(&ctl->v_empty[i], 1);
+      mbar_init(&ctl->s_full[i], 1);
+      mbar_init(&ctl->s_empty[i], 4);
+    }
+    mbar_init(&ctl->p_ready, 4);
+    mbar_init(&ctl->pv_done, 1);
+    fence_mbar_init();
+    fence_proxy_async();
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_g);
+  }
+  if (warp == 1) {
+    tmem_alloc(&ctl->tmem_base, 512);
+    tmem_relinquish();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = ctl->tmem_base;
+  const uint32_t tm_s0 = tmem, tm_o = tmem + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&ctl->q_full, kQBytes);
+      tma_load_2d(q_sm, &tm_x, &ctl->q_full, 0, n * Lp + q0);
+      tma_load_2d(q_sm + kQT * 128, &tm_x, &ctl->q_full, 64, n * Lp + q0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j & 1, ph = (j >> 1) & 1;
+        mbar_wait(&ctl->k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&ctl->k_full[st], kKBytes);
+        tma_load_2d(k_sm + st * kKBytes, &tm_x, &ctl->k_full[st], 0, n * Lp + j * kKT);
+        tma_load_2d(k_sm + st * kKBytes + kKT * 128, &tm_x, &ctl->k_full[st], 64, n * Lp + j * kKT);
+        mbar_wait(&ctl->v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&ctl->v_full[st], kVBytes);
+        tma_load_2d(v_sm + st * kVBytes, &tm_g, &ctl->v_full[st], j * kKT, n * kVR);
+        tma_load_2d(v_sm + st * kVBytes + kVR * 128, &tm_g, &ctl->v_full[st], j * kKT + 64, n * kVR);
+      }
+    }
+  } else if (warp == 1) {
+    // converged warp, one elected lane issues (see conv_tc.cu); descriptors advance by constant adds
+    constexpr uint32_t idesc_s = make_idesc_f16(128, 128);
+    constexpr uint32_t idesc_o = make_idesc_f16(128, kVR);
+    const uint64_t qd = make_sdesc_sw128(smem_u32(q_sm), 1024, 0);
+    const uint64_t pd = make_sdesc_sw128(smem_u32(p_sm), 1024, 0);
+    auto issue_s = [&](int j) {
+      const int st = j & 1, ph = (j >> 1) & 1;
+      mbar_wait(&ctl->k_full[st], ph);
+      mbar_wait(&ctl->s_empty[st], ph ^ 1);
+      fence_after_sync();
+      const uint64_t kd = make_sdesc_sw128(smem_u32(k_sm + st * kKBytes), 1024, 0);
+      if (elect_one_nl()) {
+        // channels 0..63 (block 0, 4 k-steps) and 64..95 (block 1, 2 k-steps; 96..127 are zero padding)
+#pragma unroll
+        for (int ks = 0; ks < 6; ++ks) {
+          const uint32_t off = ((ks < 4) ? ks * 32 : (kQT * 128 + (ks - 4) * 32)) >> 4;
+          mma_f16(tm_s0 + st * 128, qd + off, kd + off, idesc_s, ks > 0 ? 1u : 0u);
+        }
+        mma_commit(&ctl->k_empty[st]);
+        mma_commit(&ctl->s_full[st]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(&ctl->q_full, 0);
+    issue_s(0);
+    for (int j = 0; j < ntiles; ++j) {
+      if (j + 1 < ntiles) issue_s(j + 1);
+      const int st = j & 1, ph = (j >> 1) & 1;
+      mbar_wait(&ctl->v_full[st], ph);
+      mbar_wait(&ctl->p_ready, j & 1);
+      fence_after_sync();
+      const uint64_t vd = make_sdesc_sw128(smem_u32(v_sm + st * kVBytes), 1024, 0);
+      if (elect_one_nl()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t aoff = ((ks >> 2) * (kQT * 128) + (ks & 3) * 32) >> 4;
+          const uint32_t boff = ((ks >> 2) * (kVR * 128) + (ks & 3) * 32) >> 4;
+          mma_f16(tm_o, pd + aoff, vd + boff, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+        }
+        mma_commit(&ctl->v_empty[st]);
+        mma_commit(&ctl->pv_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // softmax / correction / epilogue: thread <-> query row
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < ntiles; ++j) {
+      const int st = j & 1, ph = (j >> 1) & 1;
+      mbar_wait(&ctl->s_full[st], ph);
+      fence_after_sync();
+      const int kvalid = L - j * kKT;  // keys >= kvalid in this tile are padding
+      float mt = -INFINITY;
+      uint32_t sreg[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tm_s0 + st * 128 + lane_addr + c * 32, sreg[c]);
+      tmem_ld_wait();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->s_empty[st]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(sreg[c][i]);
+          if (c * 32 + i >= kvalid) s = -INFINITY;
+          sreg[c][i] = __float_as_uint(s);
+          mt = fmaxf(mt, s);
+        }
+      const float m_new = fmaxf(m_run, mt);   // finite: every tile holds at least one valid key
+      const float alpha = __expf(m_run - m_new);
+      m_run = m_new;
+      float psum = 0.f;
+      // previous PV must be complete before P is overwritten and before O is rescaled
+      if (j > 0) {
+        mbar_wait(&ctl->pv_done, (j - 1) & 1);
+        fence_after_sync();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(tm_o + lane_addr + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x32(tm_o + lane_addr + c * 32, o);
+          }
+          tmem_st_wait();
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          __align__(16) __half hp[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float pv = __expf(__uint_as_float(sreg[c][g8 * 8 + i]) - m_new);
+            hp[i] = __float2half_rn(pv);
+            psum += __half2float(hp[i]);
+          }
+          const int chunk = c * 4 + g8;  // 16-byte chunk index along the 128 keys
+          const uint32_t off = (chunk >> 3) * (kQT * 128) + sw128_offset(row, chunk & 7);
+          *reinterpret_cast<uint4*>(p_sm + off) = *reinterpret_cast<const uint4*>(hp);
+        }
+      }
+      l_run = l_run * alpha + psum;
+      fence_proxy_async();   // make the generic-proxy P writes visible to the tensor-core (async) proxy
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->p_ready);
+    }
+    mbar_wait(&ctl->pv_done, (ntiles - 1) & 1);
+    fence_after_sync();
+    const int q = q0 + row;
+    const float inv = 1.f / l_run;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tm_o + lane_addr + c * 32, o);
+      tmem_ld_wait();
+      if (q < L) {
+        float* dst = Y + ((long long)n * L + q) * kNL + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          if (c * 32 + i < kNL)
+            *reinterpret_cast<float4*>(dst + i) =
+                make_float4(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv,
+                            __uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// X fp32 [N,L,84] -> X16 [N,Lp,128] (zero padded) and Gt16 [N,96,Lp] = (X*Wg+bg)^T (zero padded).
+// CTA = 64 tokens of one clip.
+__global__ void __launch_bounds__(256) nl_prep_kernel(const float* __restrict__ X, int L, int Lp,
+                                                      const float* __restrict__ Wg, const float* __restrict__ bg,
+                                                      __half* __restrict__ X16, __half* __restrict__ Gt16) {
+  __shared__ __align__(16) float xs[64 * kNL];
+  __shared__ __align__(16) float gs[64 * (kVR + 1)];
+  const int tid = threadIdx.x;
+  const int n = blockIdx.y, t0 = blockIdx.x * 64;
+  const float* Xn = X + (long long)n * L * kNL;
+  for (int i = tid; i < 64 * kNL; i += 256) {
+    const int t = t0 + i / kNL;
+    xs[i] = t < L ? Xn[(long long)t0 * kNL + i] : 0.f;
+  }
+  __syncthreads();
+  // X16 rows (coalesced 256-byte rows)
+  for (int i = tid; i < 64 * kCP; i += 256) {
+    const int tl = i / kCP, c = i % kCP;
+    X16[((long long)n * Lp + t0 + tl) * kCP + c] = __float2half_rn(c < kNL ? xs[tl * kNL + c] : 0.f);
+  }
+  // G tile: thread -> (token tl = tid/4, 24 columns starting at (tid%4)*24)
+  {
+    const int tl = tid >> 2, cb = (tid & 3) * 24;
+    float acc[24];
+#pragma unroll
+    for (int j = 0; j < 24; ++j) acc[j] = 0.f;
+    for (int k = 0; k < kNL; ++k) {
+      const float xv = xs[tl * kNL + k];
+#pragma unroll
+      for (int j = 0; j < 24; ++j) {
+        const int c = cb + j;
+        if (c < kNL) acc[j] = fmaf(xv, Wg[k * kNL + c], acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 24; ++j) {
+      const int c = cb + j;
+      const bool valid = c < kNL && (t0 + tl) < L;
+      gs[tl * (kVR + 1) + c] = valid ? acc[j] + bg[c] : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < kVR * 64; i += 256) {
+    const int c = i >> 6, tl = i & 63;
+    Gt16[((long long)n * kVR + c) * Lp + t0 + tl] = __float2half_rn(gs[tl * (kVR + 1) + c]);
+  }
+}
+
+struct NlScratch {
+  __half* x16 = nullptr;
+  __half* gt16 = nullptr;
+  float* y = nullptr;
+  size_t cap_tokens = 0;  // N*Lp capacity
+};
+
+}  // namespace
+
+bool tc_has_nonlocal() { return true; }
+
+int tc_nl_init() {
+  PFNL_CUDA(cudaFuncSetAttribute(nl_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNlSmem));
+  return PFNL_OK;
+}
+
+static int run_nl_tc(const float* tokens, int N, int L, __half* x16, __half* gt16, float* Y, const float* Wg,
+                     const float* bg, cudaStream_t s) {
+  const int Lp = ceil_div(L, kKT) * kKT;
+  dim3 pg(Lp / 64, N);
+  nl_prep_kernel<<<pg, 256, 0, s>>>(tokens, L, Lp, Wg, bg, x16, gt16);
+  PFNL_LAUNCH_CHECK();
+  CUtensorMap tmx, tmg;
+  int r = make_mat_tmap(&tmx, x16, (uint64_t)N * Lp, kCP, kQT);
+  if (r == 0) r = make_mat_tmap(&tmg, gt16, (uint64_t)N * kVR, (uint64_t)Lp, kVR);
+  if (r != 0) {
+    set_error("non-local tensor map encode failed (%d)", r);
+    return PFNL_ERR_CUDA;
+  }
+  dim3 grid(Lp / kQT, N);
+  nl_tc_kernel<<<grid, 192, kNlSmem, s>>>(tmx, tmg, L, Lp, Y);
+  PFNL_LAUNCH_CHECK();
+  return PFNL_OK;
+}
+
+size_t tc_nl_workspace_bytes(int N, int L) {
+  const size_t Lp = (size_t)ceil_div(L, kKT) * kKT;
+  return N * Lp * kCP * 2 + 1024 + (size_t)N * kVR * Lp * 2 + 1024;
+}
+
+int tc_nonlocal(const TcWeights& tw, TcWorkspace& w, const float* tokens, const float* lr, int N, int H, int W,
+                float* inp21, cudaStream_t s, long long* launches, Profiler* prof) {
+  const int L = (H / 2) * (W / 2);
+  const size_t Lp = (size_t)ceil_div(L, kKT) * kKT;
+  __half* x16 = (__half*)w.nl_x16;
+  __half* gt16 = (__half*)((uint8_t*)w.nl_x16 + (N * Lp * kCP * 2 + 1023) / 1024 * 1024);
+  float* y = (float*)w.nl_priv;
+  if (prof) prof->begin(kProfNonlocal, s);
+  int rc = run_nl_tc(tokens, N, L, x16, gt16, y, tw.raw.nl_g_w, tw.raw.nl_g_b, s);
+  if (rc == PFNL_OK) rc = launch_nl_linear_scatter(y, lr, N, H, W, tw.raw.nl_w_w, tw.raw.nl_w_b, inp21, s);
+  if (prof) prof->end(s);
+  if (rc) return rc;
+  *launches += 3;
+  return PFNL_OK;
+}
+
+int tc_nonlocal_tokens(const TcWeights& tw, const float* tokens, int N, int L, float* out, cudaStream_t s,
+                       long long* launches) {
+  // stage-level entry (pfnl_nonlocal): scratch is allocated per call (isolation benchmarks only)
+  const size_t Lp = (size_t)ceil_div(L, kKT) * kKT;
+  __half *x16 = nullptr, *gt16 = nullptr;
+  float* y = nullptr;
+  PFNL_CUDA(cudaMallocAsync((void**)&x16, N * Lp * kCP * 2, s));
+  PFNL_CUDA(cudaMallocAsync((void**)&gt16, (size_t)N * kVR * Lp * 2, s));
+  PFNL_CUDA(cudaMallocAsync((void**)&y, (size_t)N * L * kNL * 4, s));
+  int rc = run_nl_tc(tokens, N, L, x16, gt16, y, tw.raw.nl_g_w, tw.raw.nl_g_b, s);
+  if (rc == PFNL_OK) rc = launch_nl_linear(y, N * L, tw.raw.nl_w_w, tw.raw.nl_w_b, out, s);
+  cudaFreeAsync(x16, s);
+  cudaFreeAsync(gt16, s);
+  cudaFreeAsync(y, s);
+  if (rc) return rc;
+  *launches += 3;
+  return PFNL_OK;
 }
 
 }  // namespace pfnl

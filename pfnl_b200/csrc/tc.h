@@ -68,6 +68,8 @@ void tc_destroy(TcWeights& tw);
 int tc_trunk(const TcWeights& tw, TcWorkspace& w, int precision, const float* inp21, int N, int H, int W,
              float* merge, cudaStream_t s, long long* launches, Profiler* prof);
 bool tc_has_nonlocal();
+int tc_nl_init();                               // per-device kernel attributes
+size_t tc_nl_workspace_bytes(int N, int L);     // X16 + Gt16 staging of the tensor-core non-local block
 // tokens [N,L,84] (+ lr for the residual) -> inp21 [N,H,W,21]   (model/pfnl.py:58-60)
 int tc_nonlocal(const TcWeights& tw, TcWorkspace& w, const float* tokens, const float* lr, int N, int H, int W,
                 float* inp21, cudaStream_t s, long long* launches, Profiler* prof);

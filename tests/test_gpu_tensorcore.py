@@ -94,6 +94,47 @@ def test_forward_fp16_single_pass_tolerance(tc_engines):
     assert eA <= 2e-2 * np.abs(refA).max()
 
 
+@pytest.mark.parametrize("hh,ww,n", [(16, 16, 2), (8, 8, 3), (10, 6, 2), (13, 10, 1), (32, 32, 1), (64, 64, 1), (1, 1, 1)])
+def test_nonlocal_tcgen05_vs_oracle(tc_engines, hh, ww, n):
+    """tcgen05 non-local block (fp16 operands, fp32 accumulate, online softmax) vs the fp64 oracle:
+    L = 256, 64, 60 (ragged), 130 (ragged), 1024, 4096 and the degenerate L = 1.
+    Tolerance 4e-3 abs on |y| <~ 2.5 (fp16 rounding of X perturbs the logits by ~1e-3 relative)."""
+    W = R.make_weights("B")
+    P = "nlvsr/nlblock_0/"
+    rng = np.random.default_rng(hh * 100 + ww)
+    t = rng.random((n, hh, ww, 84), dtype=np.float32)
+    ref = R.nonlocal_block(t.astype(np.float64), *(W[P + s].astype(np.float64) for s in
+                                                   ("g/g/kernel", "g/g/bias", "w/w/kernel", "w/w/bias")), stable=True)
+    out = tc_engines[("fp16", "B")].nonlocal_block(cu(t.reshape(n, hh * ww, 84))).cpu().numpy().reshape(n, hh, ww, 84)
+    err = np.abs(out - ref).max()
+    print(f"tcgen05 non-local L={hh * ww}: max-abs {err:.3e} (|ref|max {np.abs(ref).max():.2f})")
+    assert np.isfinite(out).all()
+    assert err <= 4e-3
+
+
+def test_nonlocal_tcgen05_large_logits_and_6480(tc_engines):
+    e = tc_engines[("fp16", "B")]
+    W = R.make_weights("B")
+    P = "nlvsr/nlblock_0/"
+    t = np.full((1, 2048, 84), 0.9, np.float32)          # logits 68: naive exp/sum would overflow
+    out = e.nonlocal_block(cu(t)).cpu().numpy()
+    assert np.isfinite(out).all()
+    g = t[0, :1] @ W[P + "g/g/kernel"][0, 0] + W[P + "g/g/bias"]
+    zrow = g @ W[P + "w/w/kernel"][0, 0] + W[P + "w/w/bias"]
+    np.testing.assert_allclose(out[0], np.broadcast_to(zrow, (2048, 84)), atol=4e-3)
+    rng = np.random.default_rng(9)
+    t = (rng.random((1, 6480, 84), dtype=np.float32) * 0.5).astype(np.float32)   # 90x72 token grid
+    out = e.nonlocal_block(cu(t)).cpu().numpy()
+    rows = [0, 1234, 6479]
+    x64 = t[0].astype(np.float64)
+    s = x64[rows] @ x64.T
+    p = np.exp(s - s.max(1, keepdims=True))
+    p /= p.sum(1, keepdims=True)
+    g = x64 @ W[P + "g/g/kernel"][0, 0].astype(np.float64) + W[P + "g/g/bias"]
+    ref = (p @ g) @ W[P + "w/w/kernel"][0, 0].astype(np.float64) + W[P + "w/w/bias"]
+    np.testing.assert_allclose(out[0, rows], ref, atol=4e-3)
+
+
 def test_forward_batch16_tc_matches_per_clip(tc_engines):
     x = R.make_input(16, 32, 32, seed=99)
     e = tc_engines[("fp16x3", "B")]
