@@ -19,9 +19,10 @@
 // padding and base_offset = 0; probes/umma_probe.cu.)
 // Weights ([taps][N][64] fp16, pre-swizzled) stay resident in smem for the CTA's lifetime.
 //
-// Warp roles (192 threads, 1 CTA / SM, persistent over tiles): warp 0 = TMA producer, warp 1 =
-// MMA issuer (converged warp, one elected lane issues), warps 2-5 = epilogue (tcgen05.ld -> bias /
-// leaky_relu / partial sums / residual -> fp16 planes or fp32).  TMEM accumulators are double
+// Warp roles (576 threads, 1 CTA / SM, persistent over tiles): warp 0 = TMA producer, warp 1 =
+// MMA issuer (converged warp, one elected lane issues), warps 2-17 = epilogue (tcgen05.ld -> bias /
+// leaky_relu / partial sums / residual -> fp16 planes or fp32; 16 warps so that conversion/ALU
+// latency is hidden - with 4 warps the epilogue, not the MMAs, set the tile time).  TMEM accumulators are double
 // buffered so the epilogue of tile i overlaps the MMAs of tile i+1.  Launched with programmatic
 // dependent launch: the prologue (barriers, TMEM alloc, weight load) overlaps the previous
 // kernel's tail; griddepcontrol.wait guards every access to activations.
@@ -46,6 +47,8 @@ enum TcEpi {
 
 struct TcConvParams {
   int H, W, tiles_x, tiles_y, n_tiles;
+  int frames, n_units;   // work unit = one spatial tile x `frames` consecutive output images (7 when the
+                         // output is per-frame: the CTA keeps the unit's shared partial sums in registers)
   int img_mul, img_add;  // source image coordinate of stage s = out_img*img_mul + img_add + s
   int epi;
   int accumulate;        // kEpiPartialF32: add the previous content of out_f32
@@ -57,7 +60,14 @@ struct TcConvParams {
   const __half* res_hi;
   const __half* res_lo;
   float* out_f32;        // [out_images][H][W][NOUT]
+  long long* trace;      // debug (PFNL_TC_TRACE=1): clock64 stamps of CTA 0, [role][event] ; else NULL
 };
+
+// trace slots: role 0 producer, 1 MMA issuer, 2 epilogue warp 2; 64 events per role
+#define TC_TRACE(role, ev)                                                                  \
+  do {                                                                                      \
+    if (p.trace != nullptr && blockIdx.x == 0 && (ev) < 64) p.trace[(role) * 64 + (ev)] = clock64(); \
+  } while (0)
 
 template <int KS, int NSRC, int NSPLIT, int NOUT, int NCH>
 struct TcCfg {
@@ -73,23 +83,27 @@ struct TcCfg {
   static constexpr int CTRL_BYTES = 1024;
   static constexpr int BUDGET = SMEM_MAX - 1024 /*align slack*/ - CTRL_BYTES - W_BYTES;
   static constexpr int TOTAL_SLOTS = BUDGET / SLOT_BYTES;
-  static constexpr int NL = NSPLIT == 1 ? 0 : (TOTAL_SLOTS / 2 > 3 ? 3 : TOTAL_SLOTS / 2);
-  static constexpr int NH = (TOTAL_SLOTS - NL) > 4 ? 4 : (TOTAL_SLOTS - NL);
-  static constexpr int SMEM_BYTES = 1024 + CTRL_BYTES + W_BYTES + (NH + NL) * SLOT_BYTES;
+  // ONE ring of patch slots shared by the hi and lo planes (loads alternate lo, hi, lo, hi ...):
+  // with 3 slots every TMA load is issued >= one full plane pass (1.7-3.5 K cycles) before the
+  // MMAs need it, which hides the ~2 us (4 K cycle) load latency seen under full-chip load.
+  static constexpr int NS = TOTAL_SLOTS > 6 ? 6 : TOTAL_SLOTS;
+  static constexpr int SMEM_BYTES = 1024 + CTRL_BYTES + W_BYTES + NS * SLOT_BYTES;
   // TMEM per accumulator buffer: NCH chains of D0 (+ D1 in the split mode), 64 columns each
   static constexpr int D1_COL = NCH * 64;
   static constexpr int TMEM_BUF_COLS = (NCH + (NSPLIT == 2 ? 1 : 0)) * 64;
   static constexpr int TMEM_NEED = 2 * TMEM_BUF_COLS;
   static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
   static_assert(TMEM_NEED <= 512, "TMEM overflow");
-  static_assert(NH >= 1 && (NSPLIT == 1 || NL >= 1), "shared memory budget too small");
+  static_assert(NS >= (NSPLIT == 2 ? 2 : 1), "shared memory budget too small");
   static_assert(SMEM_BYTES <= SMEM_MAX, "shared memory overflow");
 };
 
+constexpr int kTcEpiWarps = 16;                    // 4 TMEM lane quarters x 4 sixteen-channel chunks
+constexpr int kTcThreads = (2 + kTcEpiWarps) * 32;  // + producer warp + MMA warp = 576
+
 struct TcCtrl {
   uint64_t wfull;
-  uint64_t full_hi[4], empty_hi[4];
-  uint64_t full_lo[4], empty_lo[4];
+  uint64_t full[8], empty[8];
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
   float bias[64];
@@ -109,20 +123,39 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per lane, half the
+// LSU requests of two 16-byte accesses for the thread-per-pixel-row pattern of the epilogue.
+struct __align__(32) U256 {
+  uint32_t w[8];
+};
+__device__ __forceinline__ U256 ld256(const void* ptr) {
+  U256 r;
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
+                 "=r"(r.w[7])
+               : "l"(ptr)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void st256(void* ptr, const U256& r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(r.w[0]), "r"(r.w[1]), "r"(r.w[2]),
+               "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]), "r"(r.w[7])
+               : "memory");
+}
+
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 template <int KS, int NSRC, int NSPLIT, int NOUT, int NCH>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kTcThreads, 1)
     conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                    const __half* __restrict__ wimg, const TcConvParams p) {
   using C = TcCfg<KS, NSRC, NSPLIT, NOUT, NCH>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* wsm = smem;                                  // [NSPLIT][NTAPS][WT_BYTES]
-  uint8_t* ring_hi = wsm + C::W_BYTES;                  // [NH][SLOT_BYTES]
-  uint8_t* ring_lo = ring_hi + C::NH * C::SLOT_BYTES;   // [NL][SLOT_BYTES]
-  TcCtrl* ctl = reinterpret_cast<TcCtrl*>(ring_lo + C::NL * C::SLOT_BYTES);
+  uint8_t* ring = wsm + C::W_BYTES;                     // [NS][SLOT_BYTES]
+  TcCtrl* ctl = reinterpret_cast<TcCtrl*>(ring + C::NS * C::SLOT_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int PAD = (KS - 1) / 2;
 
@@ -130,15 +163,13 @@ __global__ void __launch_bounds__(192, 1)
   //      kernel's tail under programmatic dependent launch
   if (tid == 0) {
     mbar_init(&ctl->wfull, 1);
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&ctl->full_hi[i], 1);
-      mbar_init(&ctl->empty_hi[i], 1);
-      mbar_init(&ctl->full_lo[i], 1);
-      mbar_init(&ctl->empty_lo[i], 1);
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&ctl->full[i], 1);
+      mbar_init(&ctl->empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl->tmem_full[i], 1);
-      mbar_init(&ctl->tmem_empty[i], 4);
+      mbar_init(&ctl->tmem_empty[i], kTcEpiWarps);
     }
     fence_mbar_init();
     fence_proxy_async();
@@ -165,32 +196,29 @@ __global__ void __launch_bounds__(192, 1)
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int sh = 0, ph = 0, sl = 0, pl = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int tx = tile % p.tiles_x;
-        const int r = tile / p.tiles_x;
+      int sl = 0, ph = 0, tcount = 0;
+      TC_TRACE(0, 0);
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x)
+      for (int t = 0; t < p.frames; ++t, ++tcount) {
+        const int tx = u % p.tiles_x;
+        const int r = u / p.tiles_x;
         const int ty = r % p.tiles_y;
-        const int img = r / p.tiles_y;
+        const int img = (r / p.tiles_y) * p.frames + t;
         const int x0 = tx * 8 - PAD, y0 = ty * 16 - PAD;
         for (int s = 0; s < NSRC; ++s) {
           const int ic = img * p.img_mul + p.img_add + s;
-          if (NSPLIT == 2) {
-            mbar_wait(&ctl->empty_lo[sl], pl ^ 1);
-            mbar_arrive_expect_tx(&ctl->full_lo[sl], C::PATCH_BYTES);
-            tma_load_4d(ring_lo + sl * C::SLOT_BYTES, &tm_lo, &ctl->full_lo[sl], 0, x0, y0, ic);
-            if (++sl == C::NL) {
+#pragma unroll
+          for (int pl = NSPLIT - 1; pl >= 0; --pl) {  // lo plane first (consumed first), then hi
+            mbar_wait(&ctl->empty[sl], ph ^ 1);
+            mbar_arrive_expect_tx(&ctl->full[sl], C::PATCH_BYTES);
+            tma_load_4d(ring + sl * C::SLOT_BYTES, pl == 1 ? &tm_lo : &tm_hi, &ctl->full[sl], 0, x0, y0, ic);
+            if (++sl == C::NS) {
               sl = 0;
-              pl ^= 1;
+              ph ^= 1;
             }
           }
-          mbar_wait(&ctl->empty_hi[sh], ph ^ 1);
-          mbar_arrive_expect_tx(&ctl->full_hi[sh], C::PATCH_BYTES);
-          tma_load_4d(ring_hi + sh * C::SLOT_BYTES, &tm_hi, &ctl->full_hi[sh], 0, x0, y0, ic);
-          if (++sh == C::NH) {
-            sh = 0;
-            ph ^= 1;
-          }
         }
+        TC_TRACE(0, 1 + tcount);
       }
     }
   } else if (warp == 1) {
@@ -204,8 +232,10 @@ __global__ void __launch_bounds__(192, 1)
     const uint64_t wd_lo = make_sdesc_sw128(smem_u32(wsm) + C::NTAPS * C::WT_BYTES, 1024, 0);
     mbar_wait(&ctl->wfull, 0);
     fence_after_sync();
-    int sh = 0, ph = 0, sl = 0, pl = 0, it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    if (lane == 0) TC_TRACE(1, 0);
+    int sl = 0, ph = 0, it = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x)
+    for (int t = 0; t < p.frames; ++t, ++it) {
       const int buf = it & 1;
       mbar_wait(&ctl->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
       fence_after_sync();
@@ -218,9 +248,9 @@ __global__ void __launch_bounds__(192, 1)
         const uint64_t wsd_lo = wd_lo + (uint64_t)((s * C::TAPS * C::WT_BYTES) >> 4);
         if (NSPLIT == 2) {
           // lo-plane pass first: its patch slot is released early and refilled under the hi pass
-          mbar_wait(&ctl->full_lo[sl], pl);
+          mbar_wait(&ctl->full[sl], ph);
           fence_after_sync();
-          const uint64_t ad = make_sdesc_sw128(smem_u32(ring_lo + sl * C::SLOT_BYTES), SBO_A, 0);
+          const uint64_t ad = make_sdesc_sw128(smem_u32(ring + sl * C::SLOT_BYTES), SBO_A, 0);
           if (elect_one()) {
 #pragma unroll
             for (int t = 0; t < C::TAPS; ++t) {
@@ -232,18 +262,19 @@ __global__ void __launch_bounds__(192, 1)
                 acc1 = 1;
               }
             }
-            mma_commit(&ctl->empty_lo[sl]);
+            mma_commit(&ctl->empty[sl]);
           }
           __syncwarp();
           acc1 = 1;
-          if (++sl == C::NL) {
+          if (++sl == C::NS) {
             sl = 0;
-            pl ^= 1;
+            ph ^= 1;
           }
         }
-        mbar_wait(&ctl->full_hi[sh], ph);
+        mbar_wait(&ctl->full[sl], ph);
         fence_after_sync();
-        const uint64_t ad = make_sdesc_sw128(smem_u32(ring_hi + sh * C::SLOT_BYTES), SBO_A, 0);
+        if (lane == 0 && s == 0) TC_TRACE(1, 1 + 2 * it);
+        const uint64_t ad = make_sdesc_sw128(smem_u32(ring + sl * C::SLOT_BYTES), SBO_A, 0);
         if (elect_one()) {
           uint32_t am = accmask;
           uint32_t a1 = acc1;
@@ -262,47 +293,81 @@ __global__ void __launch_bounds__(192, 1)
               }
             }
           }
-          mma_commit(&ctl->empty_hi[sh]);
+          mma_commit(&ctl->empty[sl]);
           if (s == NSRC - 1) mma_commit(&ctl->tmem_full[buf]);  // same thread that issued the MMAs
         }
         __syncwarp();
+        if (lane == 0 && s == NSRC - 1) TC_TRACE(1, 2 + 2 * it);
         // every lane tracks the same chain state (the elected lane may change between calls)
 #pragma unroll
         for (int t = 0; t < C::TAPS; ++t) accmask |= 1u << ((KS == 3 ? (t / KS) : s) % NCH);
         acc1 = 1;
-        if (++sh == C::NH) {
-          sh = 0;
+        if (++sl == C::NS) {
+          sl = 0;
           ph ^= 1;
         }
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..17) =====================
+    // 16 warps (4 per SM sub-partition, so ALU / conversion latency is hidden): warp -> TMEM lane
+    // quarter (warp & 3, a hardware restriction) x one 16-channel chunk ((warp-2) >> 2).  Operands
+    // that do not depend on the accumulator (fp32 partial sums, residual planes, previous fp32
+    // content) are loaded BEFORE waiting for the MMAs, so their latency hides under the tile's MMAs.
+    const int q = warp & 3;
+    const int c0 = ((warp - 2) >> 2) * 16;
+    const bool chunk_active = c0 < NOUT;
     const int m = q * 32 + lane;        // row of the tile = TMEM lane
     const int my = m >> 3, mx = m & 7;  // pixel inside the 16x8 tile
+    const bool epi_planes = p.epi == kEpiActPlanes || p.epi == kEpiResPlanes;
+    const bool epi_res = p.epi == kEpiResPlanes;
+    const bool epi_prev = (p.epi == kEpiPartialF32 && p.accumulate) || p.epi == kEpiFinalF32;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    U256 pre[2];  // 16 fp32: partial sums (kept across the unit's frames) or previous fp32 content
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pre[0].w[j] = pre[1].w[j] = 0u;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x)
+    for (int t = 0; t < p.frames; ++t, ++it) {
       const int buf = it & 1;
-      const int tx = tile % p.tiles_x;
-      const int r = tile / p.tiles_x;
+      const int tx = u % p.tiles_x;
+      const int r = u / p.tiles_x;
       const int ty = r % p.tiles_y;
-      const int img = r / p.tiles_y;
+      const int nimg = r / p.tiles_y;
+      const int img = nimg * p.frames + t;
       const int y = ty * 16 + my, x = tx * 8 + mx;
-      const bool inb = y < p.H && x < p.W;
+      const bool inb = chunk_active && y < p.H && x < p.W;
       const long long pix = ((long long)img * p.H + y) * p.W + x;
+      // ---- prefetch (independent of the accumulator) ----
+      U256 rh, rl;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rh.w[j] = rl.w[j] = 0u;
+      if (inb) {
+        if (epi_res) {
+          if (t == 0) {  // the base-half partial sums are shared by the unit's 7 frames: load once
+            const float* pb = p.pbase + (((long long)nimg * p.H + y) * p.W + x) * 64 + c0;
+            pre[0] = ld256(pb);
+            pre[1] = ld256(pb + 8);
+          }
+          rh = ld256(p.res_hi + pix * 64 + c0);
+          if (NSPLIT == 2) rl = ld256(p.res_lo + pix * 64 + c0);
+        } else if (epi_prev) {
+          const float* o = p.out_f32 + pix * NOUT + c0;
+          pre[0] = ld256(o);
+          pre[1] = ld256(o + 8);
+        }
+      }
       mbar_wait(&ctl->tmem_full[buf], (it >> 1) & 1);
       fence_after_sync();
-      const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + buf * C::TMEM_BUF_COLS;
-#pragma unroll
-      for (int c0 = 0; c0 < NOUT; c0 += 16) {
+      if (warp == 2 && lane == 0) TC_TRACE(2, 2 * it);
+      float v[16];
+      if (chunk_active) {
+        const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + buf * C::TMEM_BUF_COLS + c0;
         uint32_t r0[16], r1[16], r2[16], r3[16];
-        tmem_ld_32x32b_x16(t0 + c0, r0);
-        if (NCH >= 2) tmem_ld_32x32b_x16(t0 + 64 + c0, r2);
-        if (NCH >= 3) tmem_ld_32x32b_x16(t0 + 128 + c0, r3);
-        if (NSPLIT == 2) tmem_ld_32x32b_x16(t0 + C::D1_COL + c0, r1);
+        tmem_ld_32x32b_x16(t0, r0);
+        if (NCH >= 2) tmem_ld_32x32b_x16(t0 + 64, r2);
+        if (NCH >= 3) tmem_ld_32x32b_x16(t0 + 128, r3);
+        if (NSPLIT == 2) tmem_ld_32x32b_x16(t0 + C::D1_COL, r1);
         tmem_ld_wait();
-        float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           v[j] = __uint_as_float(r0[j]);
@@ -310,88 +375,61 @@ __global__ void __launch_bounds__(192, 1)
           if (NCH >= 3) v[j] += __uint_as_float(r3[j]);
           if (NSPLIT == 2) v[j] = fmaf(__uint_as_float(r1[j]), 1.f / 2048.f, v[j]);
         }
-        if (inb) {
-          if (p.epi == kEpiActPlanes || p.epi == kEpiResPlanes) {
-            if (p.epi == kEpiResPlanes) {
-              const float4* pb = reinterpret_cast<const float4*>(
-                  p.pbase + (((long long)(img / p.pb_div) * p.H + y) * p.W + x) * 64 + c0);
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 t = pb[j4];
-                v[4 * j4 + 0] += t.x;
-                v[4 * j4 + 1] += t.y;
-                v[4 * j4 + 2] += t.z;
-                v[4 * j4 + 3] += t.w;
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = lrelu(v[j] + ctl->bias[c0 + j]);
-            if (p.epi == kEpiResPlanes) {
-              const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + pix * 64 + c0);
-              const uint4 a0 = rh[0], a1 = rh[1];
-              const __half* hh0 = reinterpret_cast<const __half*>(&a0);
-              const __half* hh1 = reinterpret_cast<const __half*>(&a1);
-              if (NSPLIT == 2) {
-                // residual = hi + lo/2048 (exactly representable in fp32), then one rounded add
-                const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + pix * 64 + c0);
-                const uint4 b0 = rl[0], b1 = rl[1];
-                const __half* hl0 = reinterpret_cast<const __half*>(&b0);
-                const __half* hl1 = reinterpret_cast<const __half*>(&b1);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  v[j] += fmaf(__half2float(hl0[j]), 1.f / 2048.f, __half2float(hh0[j]));
-                  v[8 + j] += fmaf(__half2float(hl1[j]), 1.f / 2048.f, __half2float(hh1[j]));
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  v[j] += __half2float(hh0[j]);
-                  v[8 + j] += __half2float(hh1[j]);
-                }
-              }
-            }
-            __align__(16) __half oh[16];
-            __align__(16) __half ol[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (NSPLIT == 2)
-                split_half(v[j], oh[j], ol[j]);
-              else
-                oh[j] = __float2half_rn(v[j]);
-            }
-            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + pix * 64 + c0);
-            dh[0] = reinterpret_cast<const uint4*>(oh)[0];
-            dh[1] = reinterpret_cast<const uint4*>(oh)[1];
-            if (NSPLIT == 2) {
-              uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * 64 + c0);
-              dl[0] = reinterpret_cast<const uint4*>(ol)[0];
-              dl[1] = reinterpret_cast<const uint4*>(ol)[1];
-            }
-          } else {
-            float4* o = reinterpret_cast<float4*>(p.out_f32 + pix * NOUT + c0);
-            if ((p.epi == kEpiPartialF32 && p.accumulate) || p.epi == kEpiFinalF32) {
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 t = o[j4];
-                v[4 * j4 + 0] += t.x;
-                v[4 * j4 + 1] += t.y;
-                v[4 * j4 + 2] += t.z;
-                v[4 * j4 + 3] += t.w;
-              }
-            }
-            if (p.epi == kEpiFinalF32) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = lrelu(v[j] + ctl->bias[c0 + j]);
-            }
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) o[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-          }
-        }
       }
-      // all tcgen05.ld of this warp have completed (wait::ld above): hand the TMEM buffer back
+      // this warp's tcgen05.ld are complete: hand the TMEM buffer back before the global stores
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->tmem_empty[buf]);
+      if (inb) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // + partial sums / previous content (zeros otherwise)
+          v[j] += __uint_as_float(pre[0].w[j]);
+          v[8 + j] += __uint_as_float(pre[1].w[j]);
+        }
+        if (epi_planes) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = lrelu(v[j] + ctl->bias[c0 + j]);
+          if (epi_res) {
+            const __half* hh = reinterpret_cast<const __half*>(&rh);
+            if (NSPLIT == 2) {
+              // residual = hi + lo/2048 (exactly representable in fp32), then one rounded add
+              const __half* hl = reinterpret_cast<const __half*>(&rl);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += fmaf(__half2float(hl[j]), 1.f / 2048.f, __half2float(hh[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += __half2float(hh[j]);
+            }
+          }
+          U256 oh, ol;
+          __half* ph = reinterpret_cast<__half*>(&oh);
+          __half* pl = reinterpret_cast<__half*>(&ol);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (NSPLIT == 2)
+              split_half(v[j], ph[j], pl[j]);
+            else
+              ph[j] = __float2half_rn(v[j]);
+          }
+          st256(p.out_hi + pix * 64 + c0, oh);
+          if (NSPLIT == 2) st256(p.out_lo + pix * 64 + c0, ol);
+        } else {
+          if (p.epi == kEpiFinalF32) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = lrelu(v[j] + ctl->bias[c0 + j]);
+          }
+          U256 o0, o1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            o0.w[j] = __float_as_uint(v[j]);
+            o1.w[j] = __float_as_uint(v[8 + j]);
+          }
+          float* o = p.out_f32 + pix * NOUT + c0;
+          st256(o, o0);
+          st256(o + 8, o1);
+        }
+      }
+      if (warp == 2 && lane == 0) TC_TRACE(2, 2 * it + 1);
     }
   }
   fence_before_sync();
@@ -519,6 +557,12 @@ namespace {
 
 int g_num_sms = 0;
 int g_chains = -1;
+bool g_pdl = true;
+
+bool pdl_enabled() {
+  static const bool env_off = getenv("PFNL_TC_NO_PDL") != nullptr;
+  return g_pdl && !env_off;
+}
 
 // x3 mode: number of D0 accumulation chains of the 3x3 kernels (1 or 3; PFNL_TC_CHAINS overrides)
 int x3_chains() {
@@ -543,20 +587,44 @@ int launch_tc_impl(const void* src_hi, const void* src_lo, int src_images, const
   p.tiles_x = ceil_div(p.W, 8);
   p.tiles_y = ceil_div(p.H, 16);
   p.n_tiles = out_images * p.tiles_x * p.tiles_y;
+  if (p.frames < 1) p.frames = 1;
+  p.n_units = p.n_tiles / p.frames;
   if (p.n_tiles <= 0) return PFNL_OK;
-  const int grid = p.n_tiles < g_num_sms ? p.n_tiles : g_num_sms;
+  const int grid = p.n_units < g_num_sms ? p.n_units : g_num_sms;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  static long long* trace_dev = nullptr;
+  static const bool tracing = getenv("PFNL_TC_TRACE") != nullptr;
+  if (tracing) {
+    if (!trace_dev) PFNL_CUDA(cudaMalloc((void**)&trace_dev, 3 * 64 * sizeof(long long)));
+    PFNL_CUDA(cudaMemsetAsync(trace_dev, 0, 3 * 64 * sizeof(long long), s));
+    p.trace = trace_dev;
+  }
   PFNL_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<KS, NSRC, NSPLIT, NOUT, NCH>, tmh, tml, wimg, p));
+  if (tracing) {
+    long long t[3 * 64];
+    PFNL_CUDA(cudaStreamSynchronize(s));
+    PFNL_CUDA(cudaMemcpy(t, trace_dev, sizeof(t), cudaMemcpyDeviceToHost));
+    const long long t0 = t[0];
+    fprintf(stderr, "[tc-trace] KS=%d NSRC=%d NSPLIT=%d NOUT=%d NCH=%d epi=%d tiles=%d grid=%d (cycles since producer start)\n",
+            KS, NSRC, NSPLIT, NOUT, NCH, p.epi, p.n_tiles, grid);
+    fprintf(stderr, "  producer issue done :");
+    for (int i = 1; i < 12 && t[i]; ++i) fprintf(stderr, " %lld", t[i] - t0);
+    fprintf(stderr, "\n  mma: weights ready %lld ; per tile (data ready, issue done):", t[64] - t0);
+    for (int i = 0; i < 10 && t[64 + 1 + 2 * i]; ++i) fprintf(stderr, " (%lld,%lld)", t[64 + 1 + 2 * i] - t0, t[64 + 2 + 2 * i] - t0);
+    fprintf(stderr, "\n  epilogue per tile (acc ready, done):");
+    for (int i = 0; i < 10 && t[128 + 2 * i]; ++i) fprintf(stderr, " (%lld,%lld)", t[128 + 2 * i] - t0, t[128 + 1 + 2 * i] - t0);
+    fprintf(stderr, "\n");
+  }
   return PFNL_OK;
 }
 
@@ -674,6 +742,8 @@ int tc_init(TcWeights& tw, int precision, const TcRawWeights& raw, std::vector<v
 
 void tc_destroy(TcWeights&) {}
 
+void tc_set_pdl(bool on) { g_pdl = on; }
+
 namespace {
 
 // One PFRB (model/pfnl.py:66-71) on fp16 planes, in place on actA.
@@ -688,6 +758,7 @@ int pfrb_tc(const TcWeights& tw, TcWorkspace& w, int i, int N, int H, int W, cud
   // inp1[t] = conv1_i(inp0[t])                                   pfnl.py:66
   p.img_mul = 1;
   p.img_add = 0;
+  p.frames = kFrames;  // unit = spatial tile x 7 frames
   p.epi = kEpiActPlanes;
   p.bias = tw.raw.conv1_b[i];
   p.out_hi = (__half*)w.actB[0];
@@ -698,6 +769,7 @@ int pfrb_tc(const TcWeights& tw, TcWorkspace& w, int i, int N, int H, int W, cud
   if (rc) return rc;
   // base = conv10_i(concat_t inp1[t])                            pfnl.py:67-68  (7 K-slices, no concat copy)
   p.img_mul = kFrames;
+  p.frames = 1;
   p.bias = tw.raw.conv10_b[i];
   p.out_hi = (__half*)w.base[0];
   p.out_lo = (__half*)w.base[1];
@@ -718,6 +790,7 @@ int pfrb_tc(const TcWeights& tw, TcWorkspace& w, int i, int N, int H, int W, cud
   if (rc) return rc;
   // inp0[t] += leaky_relu(partial + conv(inp1[t]) + bias)         pfnl.py:70-71
   p.epi = kEpiResPlanes;
+  p.frames = kFrames;
   p.bias = tw.raw.conv2_b[i];
   p.pbase = w.pbase;
   p.pb_div = kFrames;

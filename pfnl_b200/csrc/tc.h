@@ -63,6 +63,9 @@ struct TcWorkspace {
 void tc_carve(TcWorkspace& w, int precision, int N, int H, int W, const std::function<char*(size_t)>& take);
 int tc_init(TcWeights& tw, int precision, const TcRawWeights& raw, std::vector<void*>& allocs);
 void tc_destroy(TcWeights& tw);
+// Programmatic dependent launch on/off (off while pfnl_profile brackets launches with events, so
+// that per-kernel durations do not overlap).
+void tc_set_pdl(bool on);
 
 // conv0 .. convmerge1 (model/pfnl.py:61-74): inp21 [N,H,W,21] fp32 -> merge [N,H,W,48] fp32
 int tc_trunk(const TcWeights& tw, TcWorkspace& w, int precision, const float* inp21, int N, int H, int W,
