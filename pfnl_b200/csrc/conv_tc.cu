@@ -77,8 +77,9 @@ struct TcCfg {
   static constexpr int BOX_H = KS == 3 ? 18 : 16;
   static constexpr int PATCH_BYTES = BOX_W * BOX_H * 128;
   static constexpr int SLOT_BYTES = (PATCH_BYTES + 1023) / 1024 * 1024;
-  static constexpr int WT_BYTES = NOUT * 128;
-  static constexpr int W_BYTES = NSPLIT * NTAPS * WT_BYTES;
+  static constexpr int WT_BYTES = NOUT * 128;            // one plane of one tap: [NOUT rows][64 ci]
+  static constexpr int TAP_BYTES = NSPLIT * WT_BYTES;    // split mode: [W_hi ; W_lo] stacked -> one N = 2*NOUT tile
+  static constexpr int W_BYTES = NTAPS * TAP_BYTES;
   static constexpr int SMEM_MAX = 227 * 1024;
   static constexpr int CTRL_BYTES = 1024;
   static constexpr int BUDGET = SMEM_MAX - 1024 /*align slack*/ - CTRL_BYTES - W_BYTES;
@@ -88,9 +89,9 @@ struct TcCfg {
   // MMAs need it, which hides the ~2 us (4 K cycle) load latency seen under full-chip load.
   static constexpr int NS = TOTAL_SLOTS > 6 ? 6 : TOTAL_SLOTS;
   static constexpr int SMEM_BYTES = 1024 + CTRL_BYTES + W_BYTES + NS * SLOT_BYTES;
-  // TMEM per accumulator buffer: NCH chains of D0 (+ D1 in the split mode), 64 columns each
-  static constexpr int D1_COL = NCH * 64;
-  static constexpr int TMEM_BUF_COLS = (NCH + (NSPLIT == 2 ? 1 : 0)) * 64;
+  // TMEM per accumulator buffer: NCH chains; a chain is [D0 (NOUT cols) | D1 (NOUT cols, split mode)]
+  static constexpr int CH_STRIDE = NSPLIT == 2 ? 128 : 64;
+  static constexpr int TMEM_BUF_COLS = NCH * CH_STRIDE;
   static constexpr int TMEM_NEED = 2 * TMEM_BUF_COLS;
   static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
   static_assert(TMEM_NEED <= 512, "TMEM overflow");
@@ -98,6 +99,7 @@ struct TcCfg {
   static_assert(SMEM_BYTES <= SMEM_MAX, "shared memory overflow");
 };
 
+constexpr int kPrefetchAhead = 2;                  // tiles of L2 prefetch distance in the TMA producer
 constexpr int kTcEpiWarps = 16;                    // 4 TMEM lane quarters x 4 sixteen-channel chunks
 constexpr int kTcThreads = (2 + kTcEpiWarps) * 32;  // + producer warp + MMA warp = 576
 
@@ -112,6 +114,13 @@ struct TcCtrl {
 __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
   hi = __float2half_rn(v);
   lo = __float2half_rn((v - __half2float(hi)) * 2048.f);
+}
+
+// accumulation chain of tap tp (3x3: taps 0-4 -> chain 0, 5-8 -> chain 1 when NCH = 2; one chain per
+// kernel row when NCH = 3) or of source s (1x1 over 7 sources)
+template <int KS, int NCH>
+__device__ __forceinline__ constexpr int tc_chain(int tp, int s) {
+  return NCH == 1 ? 0 : (KS == 3 ? (NCH == 2 ? (tp >= 5 ? 1 : 0) : tp / 3) : s % NCH);
 }
 
 __device__ __forceinline__ bool elect_one() {
@@ -205,10 +214,30 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const int ty = r % p.tiles_y;
         const int img = (r / p.tiles_y) * p.frames + t;
         const int x0 = tx * 8 - PAD, y0 = ty * 16 - PAD;
+        // L2 prefetch, kPrefetchAhead tiles ahead: the smem ring is only 3 slots deep in the split
+        // mode (147 KB of resident weights), not enough to cover DRAM latency under full-chip load
+        {
+          int ft = t + kPrefetchAhead, fu = u;
+          while (ft >= p.frames) {
+            ft -= p.frames;
+            fu += gridDim.x;
+          }
+          if (fu < p.n_units) {
+            const int ftx = fu % p.tiles_x;
+            const int fr = fu / p.tiles_x;
+            const int fty = fr % p.tiles_y;
+            const int fimg = (fr / p.tiles_y) * p.frames + ft;
+            for (int s = 0; s < NSRC; ++s) {
+              const int fic = fimg * p.img_mul + p.img_add + s;
+              tma_prefetch_4d(&tm_hi, 0, ftx * 8 - PAD, fty * 16 - PAD, fic);
+              if (NSPLIT == 2) tma_prefetch_4d(&tm_lo, 0, ftx * 8 - PAD, fty * 16 - PAD, fic);
+            }
+          }
+        }
         for (int s = 0; s < NSRC; ++s) {
           const int ic = img * p.img_mul + p.img_add + s;
 #pragma unroll
-          for (int pl = NSPLIT - 1; pl >= 0; --pl) {  // lo plane first (consumed first), then hi
+          for (int pl = 0; pl < NSPLIT; ++pl) {  // hi plane first (consumed first), then lo
             mbar_wait(&ctl->empty[sl], ph ^ 1);
             mbar_arrive_expect_tx(&ctl->full[sl], C::PATCH_BYTES);
             tma_load_4d(ring + sl * C::SLOT_BYTES, pl == 1 ? &tm_lo : &tm_hi, &ctl->full[sl], 0, x0, y0, ic);
@@ -226,10 +255,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // The whole warp walks the loop converged (waits are warp-uniform); one elected lane issues.
     // Descriptors are advanced by adding compile-time constants to a per-slot base descriptor:
     // ~3 instructions per tcgen05.mma instead of rebuilding two descriptors each time.
-    constexpr uint32_t idesc = make_idesc_f16(128, NOUT);
+    constexpr uint32_t idesc_lo = make_idesc_f16(128, NOUT);           // A_lo x W_hi          -> D1
+    constexpr uint32_t idesc_hi = make_idesc_f16(128, NSPLIT * NOUT);  // A_hi x [W_hi ; W_lo] -> [D0 | D1]
     constexpr uint32_t SBO_A = C::BOX_W * 128;
-    const uint64_t wd_hi = make_sdesc_sw128(smem_u32(wsm), 1024, 0);
-    const uint64_t wd_lo = make_sdesc_sw128(smem_u32(wsm) + C::NTAPS * C::WT_BYTES, 1024, 0);
+    const uint64_t wd = make_sdesc_sw128(smem_u32(wsm), 1024, 0);
     mbar_wait(&ctl->wfull, 0);
     fence_after_sync();
     if (lane == 0) TC_TRACE(1, 0);
@@ -240,72 +269,65 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       mbar_wait(&ctl->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
       fence_after_sync();
       const uint32_t dbase = tmem + buf * C::TMEM_BUF_COLS;
-      const uint32_t d1 = dbase + C::D1_COL;
-      uint32_t acc1 = 0;
-      uint32_t accmask = 0;  // bit c set once chain c has been written in this tile
+      uint32_t accmask = 0;  // bit c: chain c's block [D0|D1] has been written in this tile
       for (int s = 0; s < NSRC; ++s) {
-        const uint64_t wsd_hi = wd_hi + (uint64_t)((s * C::TAPS * C::WT_BYTES) >> 4);
-        const uint64_t wsd_lo = wd_lo + (uint64_t)((s * C::TAPS * C::WT_BYTES) >> 4);
-        if (NSPLIT == 2) {
-          // lo-plane pass first: its patch slot is released early and refilled under the hi pass
-          mbar_wait(&ctl->full[sl], ph);
-          fence_after_sync();
+        const uint64_t wsd = wd + (uint64_t)((s * C::TAPS * C::TAP_BYTES) >> 4);
+        // ---- hi-plane pass: [D0_c | D1_c] (+)= A_hi x [W_hi ; W_lo]   (one N = 2*NOUT MMA per k-step)
+        mbar_wait(&ctl->full[sl], ph);
+        fence_after_sync();
+        if (lane == 0 && s == 0) TC_TRACE(1, 1 + 2 * it);
+        {
           const uint64_t ad = make_sdesc_sw128(smem_u32(ring + sl * C::SLOT_BYTES), SBO_A, 0);
           if (elect_one()) {
+            uint32_t am = accmask;
 #pragma unroll
-            for (int t = 0; t < C::TAPS; ++t) {
+            for (int tp = 0; tp < C::TAPS; ++tp) {
+              const int ch = tc_chain<KS, NCH>(tp, s);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint32_t aoff = (((t / KS) * C::BOX_W + (t % KS)) * 128 + k * 32) >> 4;
-                const uint32_t boff = (t * C::WT_BYTES + k * 32) >> 4;
-                mma_f16(d1, ad + aoff, wsd_hi + boff, idesc, acc1);
-                acc1 = 1;
+                const uint32_t aoff = (((tp / KS) * C::BOX_W + (tp % KS)) * 128 + k * 32) >> 4;
+                const uint32_t boff = (tp * C::TAP_BYTES + k * 32) >> 4;
+                mma_f16(dbase + ch * C::CH_STRIDE, ad + aoff, wsd + boff, idesc_hi, (am >> ch) & 1u);
+                am |= 1u << ch;
               }
             }
             mma_commit(&ctl->empty[sl]);
+            if (NSPLIT == 1 && s == NSRC - 1) mma_commit(&ctl->tmem_full[buf]);
           }
           __syncwarp();
-          acc1 = 1;
+#pragma unroll
+          for (int tp = 0; tp < C::TAPS; ++tp) accmask |= 1u << tc_chain<KS, NCH>(tp, s);
           if (++sl == C::NS) {
             sl = 0;
             ph ^= 1;
           }
         }
-        mbar_wait(&ctl->full[sl], ph);
-        fence_after_sync();
-        if (lane == 0 && s == 0) TC_TRACE(1, 1 + 2 * it);
-        const uint64_t ad = make_sdesc_sw128(smem_u32(ring + sl * C::SLOT_BYTES), SBO_A, 0);
-        if (elect_one()) {
-          uint32_t am = accmask;
-          uint32_t a1 = acc1;
+        if (NSPLIT == 2) {
+          // ---- lo-plane pass: D1 of chain 0 += A_lo x W_hi (chain 0 was initialised by the hi pass:
+          //      tap 0 / source 0 always belongs to chain 0), so this always accumulates
+          mbar_wait(&ctl->full[sl], ph);
+          fence_after_sync();
+          const uint64_t ad = make_sdesc_sw128(smem_u32(ring + sl * C::SLOT_BYTES), SBO_A, 0);
+          if (elect_one()) {
 #pragma unroll
-          for (int t = 0; t < C::TAPS; ++t) {
-            const int ch = (KS == 3 ? (t / KS) : s) % NCH;
+            for (int tp = 0; tp < C::TAPS; ++tp) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t aoff = (((t / KS) * C::BOX_W + (t % KS)) * 128 + k * 32) >> 4;
-              const uint32_t boff = (t * C::WT_BYTES + k * 32) >> 4;
-              mma_f16(dbase + ch * 64, ad + aoff, wsd_hi + boff, idesc, (am >> ch) & 1u);
-              am |= 1u << ch;
-              if (NSPLIT == 2) {
-                mma_f16(d1, ad + aoff, wsd_lo + boff, idesc, a1);
-                a1 = 1;
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t aoff = (((tp / KS) * C::BOX_W + (tp % KS)) * 128 + k * 32) >> 4;
+                const uint32_t boff = (tp * C::TAP_BYTES + k * 32) >> 4;
+                mma_f16(dbase + NOUT, ad + aoff, wsd + boff, idesc_lo, 1u);
               }
             }
+            mma_commit(&ctl->empty[sl]);
+            if (s == NSRC - 1) mma_commit(&ctl->tmem_full[buf]);  // same thread that issued the MMAs
           }
-          mma_commit(&ctl->empty[sl]);
-          if (s == NSRC - 1) mma_commit(&ctl->tmem_full[buf]);  // same thread that issued the MMAs
+          __syncwarp();
+          if (++sl == C::NS) {
+            sl = 0;
+            ph ^= 1;
+          }
         }
-        __syncwarp();
         if (lane == 0 && s == NSRC - 1) TC_TRACE(1, 2 + 2 * it);
-        // every lane tracks the same chain state (the elected lane may change between calls)
-#pragma unroll
-        for (int t = 0; t < C::TAPS; ++t) accmask |= 1u << ((KS == 3 ? (t / KS) : s) % NCH);
-        acc1 = 1;
-        if (++sl == C::NS) {
-          sl = 0;
-          ph ^= 1;
-        }
       }
     }
   } else {
@@ -361,19 +383,28 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       if (warp == 2 && lane == 0) TC_TRACE(2, 2 * it);
       float v[16];
       if (chunk_active) {
+        // chain c: D0 at c*CH_STRIDE, D1 (split mode) at c*CH_STRIDE + NOUT.  Chains are summed in
+        // fp32 round-to-nearest here; D1 carries the 2^-11-scaled cross terms.
         const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + buf * C::TMEM_BUF_COLS + c0;
-        uint32_t r0[16], r1[16], r2[16], r3[16];
-        tmem_ld_32x32b_x16(t0, r0);
-        if (NCH >= 2) tmem_ld_32x32b_x16(t0 + 64, r2);
-        if (NCH >= 3) tmem_ld_32x32b_x16(t0 + 128, r3);
-        if (NSPLIT == 2) tmem_ld_32x32b_x16(t0 + C::D1_COL, r1);
+        uint32_t d0[NCH][16], d1[NSPLIT == 2 ? NCH : 1][16];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          tmem_ld_32x32b_x16(t0 + c * C::CH_STRIDE, d0[c]);
+          if (NSPLIT == 2) tmem_ld_32x32b_x16(t0 + c * C::CH_STRIDE + NOUT, d1[c]);
+        }
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          v[j] = __uint_as_float(r0[j]);
-          if (NCH >= 2) v[j] += __uint_as_float(r2[j]);
-          if (NCH >= 3) v[j] += __uint_as_float(r3[j]);
-          if (NSPLIT == 2) v[j] = fmaf(__uint_as_float(r1[j]), 1.f / 2048.f, v[j]);
+          float a = __uint_as_float(d0[0][j]);
+#pragma unroll
+          for (int c = 1; c < NCH; ++c) a += __uint_as_float(d0[c][j]);
+          if (NSPLIT == 2) {
+            float b = __uint_as_float(d1[0][j]);
+#pragma unroll
+            for (int c = 1; c < NCH; ++c) b += __uint_as_float(d1[c][j]);
+            a = fmaf(b, 1.f / 2048.f, a);
+          }
+          v[j] = a;
         }
       }
       // this warp's tcgen05.ld are complete: hand the TMEM buffer back before the global stores
@@ -442,7 +473,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 // pre-swizzled (128B) so a linear bulk copy lands them UMMA-ready.  Uses input channels
 // ci_off..ci_off+63.  plane 1 (nsplit=2) holds (w - fp16(w)) * 2048.
 __global__ void pack_tc_weights_kernel(const float* __restrict__ hwio, int taps, int cin_total, int ci_off, int cout,
-                                       int nrows, int nsplit, __half* __restrict__ out, size_t lo_plane_offset) {
+                                       int nrows, int nsplit, __half* __restrict__ out, size_t tap_stride,
+                                       size_t lo_plane_offset) {
   const int total = taps * nrows * 64;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int ci = e & 63;
@@ -451,7 +483,7 @@ __global__ void pack_tc_weights_kernel(const float* __restrict__ hwio, int taps,
     const float w = row < cout ? hwio[((long long)tap * cin_total + ci_off + ci) * cout + row] : 0.f;
     const __half hi = __float2half_rn(w);
     const uint32_t off = sw128_offset(row, ci >> 3) + (ci & 7) * 2;
-    uint8_t* base = reinterpret_cast<uint8_t*>(out) + (size_t)tap * nrows * 128;
+    uint8_t* base = reinterpret_cast<uint8_t*>(out) + (size_t)tap * tap_stride;
     *reinterpret_cast<__half*>(base + off) = hi;
     if (nsplit == 2) {
       const __half lo = __float2half_rn((w - __half2float(hi)) * 2048.f);
@@ -564,11 +596,11 @@ bool pdl_enabled() {
   return g_pdl && !env_off;
 }
 
-// x3 mode: number of D0 accumulation chains of the 3x3 kernels (1 or 3; PFNL_TC_CHAINS overrides)
+// x3 mode: number of accumulation chains of the 3x3 kernels (2, or 1 with PFNL_TC_CHAINS=1)
 int x3_chains() {
   if (g_chains < 0) {
     const char* e = getenv("PFNL_TC_CHAINS");
-    g_chains = (e && atoi(e) == 1) ? 1 : 3;
+    g_chains = (e && atoi(e) == 1) ? 1 : 2;
   }
   return g_chains;
 }
@@ -631,8 +663,8 @@ int launch_tc_impl(const void* src_hi, const void* src_lo, int src_images, const
 template <int KS, int NSRC, int NSPLIT, int NOUT>
 int launch_tc(const void* src_hi, const void* src_lo, int src_images, const __half* wimg, TcConvParams p,
               int out_images, cudaStream_t s) {
-  if (KS == 3 && NSPLIT == 2 && x3_chains() == 3)
-    return launch_tc_impl<KS, NSRC, NSPLIT, NOUT, (KS == 3 && NSPLIT == 2) ? 3 : 1>(src_hi, src_lo, src_images, wimg, p,
+  if (KS == 3 && NSPLIT == 2 && x3_chains() == 2)
+    return launch_tc_impl<KS, NSRC, NSPLIT, NOUT, (KS == 3 && NSPLIT == 2) ? 2 : 1>(src_hi, src_lo, src_images, wimg, p,
                                                                                   out_images, s);
   return launch_tc_impl<KS, NSRC, NSPLIT, NOUT, 1>(src_hi, src_lo, src_images, wimg, p, out_images, s);
 }
@@ -654,7 +686,8 @@ int pack_weights(const float* hwio, int taps, int cin_total, int ci_off, int cou
   allocs.push_back(d);
   const int total = taps * nrows * 64;
   pack_tc_weights_kernel<<<ceil_div(total, 256), 256>>>(hwio, taps, cin_total, ci_off, cout, nrows, nsplit,
-                                                       (__half*)d, (size_t)taps * nrows * 128);
+                                                       (__half*)d, (size_t)nsplit * nrows * 128,
+                                                       (size_t)nrows * 128);
   PFNL_LAUNCH_CHECK();
   *out = d;
   return PFNL_OK;
@@ -698,12 +731,12 @@ int tc_init(TcWeights& tw, int precision, const TcRawWeights& raw, std::vector<v
   int rc;
   if ((rc = set_attr<3, 1, 1, 64, 1>())) return rc;
   if ((rc = set_attr<3, 1, 2, 64, 1>())) return rc;
-  if ((rc = set_attr<3, 1, 2, 64, 3>())) return rc;
+  if ((rc = set_attr<3, 1, 2, 64, 2>())) return rc;
   if ((rc = set_attr<1, 7, 1, 64, 1>())) return rc;
   if ((rc = set_attr<1, 7, 2, 64, 1>())) return rc;
   if ((rc = set_attr<3, 1, 1, 48, 1>())) return rc;
   if ((rc = set_attr<3, 1, 2, 48, 1>())) return rc;
-  if ((rc = set_attr<3, 1, 2, 48, 3>())) return rc;
+  if ((rc = set_attr<3, 1, 2, 48, 2>())) return rc;
   if ((rc = tc_nl_init())) return rc;
   const int ns = tw.nsplit;
   for (int i = 0; i < PFNL_NUM_BLOCK; ++i) {
@@ -714,9 +747,10 @@ int tc_init(TcWeights& tw, int precision, const TcRawWeights& raw, std::vector<v
     allocs.push_back(d);
     tw.conv10[i] = d;
     for (int t = 0; t < 7; ++t) {
-      // slice t -> [plane 0][t], its lo part -> [plane 1][t]
+      // slice t -> [t][hi ; lo]
       pack_tc_weights_kernel<<<16, 256>>>(raw.conv10_w[i], 1, 448, t * 64, 64, 64, ns,
-                                          (__half*)((uint8_t*)d + (size_t)t * 8192), (size_t)7 * 8192);
+                                          (__half*)((uint8_t*)d + (size_t)t * ns * 8192), (size_t)ns * 8192,
+                                          (size_t)8192);
       PFNL_LAUNCH_CHECK();
     }
     if ((rc = pack_weights(raw.conv2_w[i], 9, 128, 0, 64, 64, ns, &tw.conv2b[i], allocs))) return rc;
@@ -732,7 +766,7 @@ int tc_init(TcWeights& tw, int precision, const TcRawWeights& raw, std::vector<v
     for (int t = 0; t < 7; ++t) {
       pack_tc_weights_kernel<<<ceil_div(9 * 48 * 64, 256), 256>>>(raw.merge1_w, 9, 448, t * 64, 48, 48, ns,
                                                                   (__half*)((uint8_t*)d + per * t),
-                                                                  (size_t)9 * 48 * 128);
+                                                                  (size_t)ns * 48 * 128, (size_t)48 * 128);
       PFNL_LAUNCH_CHECK();
     }
   }
