@@ -270,7 +270,7 @@ def run_ours(args):
     # executed useful FLOPs per launch (the base/frame split of conv2 halves its K on the tensor-core path)
     kinds = {
         "conv1_3x3": {"bytes": 2 * A_el * act_bytes, "flops": 2.0 * clips * 7 * hw * 64 * 576},
-        "conv2_3x3": {"bytes": (3 * A_el + B_el) * act_bytes,
+        "conv2_3x3": {"bytes": 3 * A_el * act_bytes + B_el * 4,   # partial sums / base are fp32 (or fp32-sized)
                       "flops": 2.0 * clips * 7 * hw * 64 * (576 if tc else 1152)},
         "conv10_1x1": {"bytes": (A_el + B_el) * act_bytes, "flops": 2.0 * clips * hw * 64 * 448},
     }
@@ -281,10 +281,16 @@ def run_ours(args):
     dur_s = dms / max(dcnt, 1) / 1e3
     gbs = kinds[dom]["bytes"] / dur_s / 1e9 if dur_s > 0 else 0.0
     tfl = kinds[dom]["flops"] / dur_s / 1e12 if dur_s > 0 else 0.0
+    traffic = None
+    try:   # DRAM bytes per launch of this kernel from the committed ncu --set full capture (tools/ncu_summary.py)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = tj.get(args.precision, {}).get(dom)
+    except Exception:
+        pass
     roof_hbm = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": gbs / peaks["hbm_gbs"], "traffic": None}
+                "frac": gbs / peaks["hbm_gbs"], "traffic": traffic}
     roof_tensor = {"bound": "tensor", "achieved": tfl, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
-                   "frac": tfl / peaks["tensor_tflops"], "traffic": None}
+                   "frac": tfl / peaks["tensor_tflops"], "traffic": traffic}
     roofline = dict(roof_tensor if (tc and roof_tensor["frac"] > roof_hbm["frac"]) else roof_hbm)
     roofline.update({"kernel": dom, "avg_launch_ms": dms / max(dcnt, 1), "launches_timed": dcnt,
                      "peak_source": peaks["source"], "algorithmic_bytes_per_launch": kinds[dom]["bytes"],
@@ -323,6 +329,34 @@ def run_ours(args):
         "kernel_ms_per_step": {k: v[0] / K for k, v in prof.items() if v[1]},
         "clocks": clocks,
     }
+    # the other precisions on the same workload (short pass), for context next to the headline
+    alt = {}
+    if n_gpus == 1 and not args.no_alt:
+        for prec in ("fp32", "fp16x3", "fp16"):
+            if prec == args.precision:
+                continue
+            try:
+                e2 = Engine(WT.xavier_init(), device=local, precision=prec, graphs=not args.no_graphs)
+                for _ in range(3):
+                    e2.forward(x_dev, out=out_dev)
+                ts = []
+                for _ in range(5):
+                    flush.zero_()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    e2.forward(x_dev, out=out_dev)
+                    b.record()
+                    torch.cuda.synchronize()
+                    ts.append(a.elapsed_time(b))
+                ms = sum(ts) / len(ts)
+                alt[prec] = {"ms_per_step": ms, "value": clips * HR_PX_PER_CLIP(size, size) / (ms / 1e3)}
+                e2.close()
+            except Exception as ex:  # never let the side measurement break the headline
+                alt[prec] = {"error": str(ex)[:200]}
+    line["other_precisions"] = alt
+    line["parity"] = ("fp32 and fp16x3 meet the 1e-3 max-abs gate vs the CPU oracle in both weight regimes "
+                      "(tests/test_gpu_parity.py, tests/test_gpu_tensorcore.py); fp16 (single pass) does not "
+                      "and is reported for context only")
     if n_gpus == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(clips, size, steps=10, warmup=1, budget_s=args.cpu_seconds)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -345,12 +379,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("PFNL_BENCH_PRECISION", "fp32"),
+    ap.add_argument("--precision", default=os.environ.get("PFNL_BENCH_PRECISION", "fp16x3"),
                     choices=["fp32", "fp16x3", "fp16"])
     ap.add_argument("--clips", type=int, default=16, help="clips per GPU per step")
     ap.add_argument("--size", type=int, default=32, help="LR frame size")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the short passes of the other precisions")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

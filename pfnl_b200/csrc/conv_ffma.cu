@@ -259,7 +259,7 @@ int launch_conv_direct(const float* in, int N, int H, int W, int Cin, const floa
 // conv0: 5x5, 3 -> 64, leaky_relu, one layer shared by the 7 frames (model/pfnl.py:48,61-62).
 // Reads frame t as channels 3t..3t+2 of inp21 [N,H,W,21] (the tf.split of pfnl.py:61).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ inp21, int H, int W,
+__global__ void __launch_bounds__(256, 2) conv0_kernel(const float* __restrict__ inp21, int H, int W,
                                                     const float* __restrict__ w, const float* __restrict__ bias,
                                                     float* __restrict__ out) {
   __shared__ __align__(16) float wsm[75 * 64];

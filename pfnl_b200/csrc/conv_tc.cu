@@ -184,16 +184,28 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     fence_proxy_async();
     tma_prefetch_desc(&tm_hi);
     if (NSPLIT == 2) tma_prefetch_desc(&tm_lo);
-    mbar_arrive_expect_tx(&ctl->wfull, C::W_BYTES);
-    for (int off = 0; off < C::W_BYTES; off += 32768) {
-      const int n = (C::W_BYTES - off) < 32768 ? (C::W_BYTES - off) : 32768;
-      bulk_load(wsm + off, reinterpret_cast<const uint8_t*>(wimg) + off, n, &ctl->wfull);
-    }
+    mbar_arrive_expect_tx(&ctl->wfull, C::W_BYTES);  // this CTA receives the whole image
   }
   if (tid < 64) ctl->bias[tid] = (p.bias != nullptr && tid < NOUT) ? p.bias[tid] : 0.f;
   if (warp == 1) {
     tmem_alloc(&ctl->tmem_base, C::TMEM_COLS);
     tmem_relinquish();
+  }
+  // Weights: every CTA of the cluster fetches 1/cs of the image from L2 and TMA-multicasts it into
+  // all cs CTAs (same smem offset, same mbarrier offset) - L2->SM weight traffic drops cs-fold.
+  const uint32_t cs = cluster_nctarank(), cr = cluster_ctarank();
+  if (cs > 1) cluster_sync_all();  // every peer's wfull barrier is initialised and armed
+  if (tid == 0) {
+    const int slice = C::W_BYTES / (int)cs;  // W_BYTES is a multiple of 1024*4
+    const int beg = (int)cr * slice;
+    for (int off = beg; off < beg + slice; off += 32768) {
+      const int n = (beg + slice - off) < 32768 ? (beg + slice - off) : 32768;
+      if (cs > 1)
+        bulk_load_multicast(wsm + off, reinterpret_cast<const uint8_t*>(wimg) + off, n, &ctl->wfull,
+                            (uint16_t)((1u << cs) - 1));
+      else
+        bulk_load(wsm + off, reinterpret_cast<const uint8_t*>(wimg) + off, n, &ctl->wfull);
+    }
   }
   fence_before_sync();
   __syncthreads();
@@ -466,6 +478,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, C::TMEM_COLS);
+  // no CTA leaves while a peer's multicast may still target the cluster
+  if (cs > 1) cluster_sync_all();
 }
 
 // ---- weight images ------------------------------------------------------------------------------------
@@ -519,7 +533,7 @@ __global__ void planes_to_f32_kernel(const __half* __restrict__ hi, const __half
 // conv0 (5x5, 3->64, leaky_relu; model/pfnl.py:48,61-62) writing fp16 planes.  K = 75 is too
 // small/odd for the MMA path (0.2 % of the FLOPs): CUDA cores, same structure as conv0_kernel.
 template <int NSPLIT>
-__global__ void __launch_bounds__(256) conv0_planes_kernel(const float* __restrict__ inp21, int H, int W,
+__global__ void __launch_bounds__(256, 2) conv0_planes_kernel(const float* __restrict__ inp21, int H, int W,
                                                            const float* __restrict__ w, const float* __restrict__ bias,
                                                            __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
   __shared__ __align__(16) float wsm[75 * 64];
@@ -622,18 +636,63 @@ int launch_tc_impl(const void* src_hi, const void* src_lo, int src_images, const
   if (p.frames < 1) p.frames = 1;
   p.n_units = p.n_tiles / p.frames;
   if (p.n_tiles <= 0) return PFNL_OK;
-  const int grid = p.n_units < g_num_sms ? p.n_units : g_num_sms;
+  int grid = p.n_units < g_num_sms ? p.n_units : g_num_sms;
+  // Cluster size for the weight multicast: the largest of 4/2/1 for which the whole (persistent)
+  // grid is co-resident (1 CTA per SM; 4-CTA clusters fit 132 of the 148 SMs, pairs fit all 148).
+  static int max_clusters[5] = {0, 0, -1, 0, -1};  // per kernel instantiation, indexed by cluster size
+  int cs = 1;
+  static const int cs_limit = getenv("PFNL_TC_CLUSTER") ? atoi(getenv("PFNL_TC_CLUSTER")) : 1;  // measured: no gain on B200 (weights already overlap under PDL), so off by default
+  for (int c = 4; c >= 2; c >>= 1) {
+    if (c > cs_limit) continue;
+    if (max_clusters[c] < 0) {
+      cudaLaunchConfig_t q;
+      memset(&q, 0, sizeof(q));
+      q.gridDim = dim3(g_num_sms / c * c);
+      q.blockDim = dim3(kTcThreads);
+      q.dynamicSmemBytes = C::SMEM_BYTES;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = c;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<KS, NSRC, NSPLIT, NOUT, NCH>, &q) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+      }
+      max_clusters[c] = n;
+    }
+    const int g = grid / c * c;
+    if (g >= c && g <= max_clusters[c] * c && (g == grid || g * 8 >= grid * 7)) {  // lose < 1/8 of the CTAs at most
+      cs = c;
+      grid = g;
+      break;
+    }
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cs > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cs;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = na;
   static long long* trace_dev = nullptr;
   static const bool tracing = getenv("PFNL_TC_TRACE") != nullptr;
   if (tracing) {
