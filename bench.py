@@ -133,7 +133,7 @@ def cpu_reference_run(clips, size, steps, warmup, budget_s=None):
         torch.set_num_threads(c)
         R.pfnl_forward(x[:2], W, backend="torch")
         t0 = time.perf_counter()
-        R.pfnl_forward(x[:2], W, backend="torch")
+        R.pfnl_forward(x, W, backend="torch")     # the full batch: small trials mis-rank thread counts
         dt = time.perf_counter() - t0
         if best is None or dt < best:
             best, cores = dt, c
@@ -299,8 +299,14 @@ def run_ours(args):
                             "stream, K steps of the same workload, L2 flushed between steps",
                      "other": roof_hbm if roofline_is(roof_tensor, tc, roof_hbm) else roof_tensor,
                      "share_of_step": shares.get(dom)})
+    if args.precision == "fp16x3":
+        roofline["tensor_executed_tflops"] = 3.0 * tfl
+        roofline["note"] = ("fp16x3 executes 3 tensor FLOPs per useful FLOP (hi*hi, hi*lo, lo*hi); 'achieved' counts "
+                            "useful FLOPs only. Measured tcgen05 law on this part (profiles/r1_mma_rate_probe.txt): "
+                            "cycles/MMA = max(N/2,40)+21.6 at M=128,K=16, i.e. a Cout=64 conv tops out at ~65% of "
+                            "nominal tensor peak in this mode")
     if not tc:
-        roofline["note"] = ("fp32 parity path: this kernel is FFMA-bound (%.1f TFLOP/s fp32 on CUDA cores), "
+        roofline["note"] =("fp32 parity path: this kernel is FFMA-bound (%.1f TFLOP/s fp32 on CUDA cores), "
                             "not HBM-bound" % tfl)
 
     total_clips = clips * n_gpus
