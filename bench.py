@@ -268,12 +268,22 @@ def run_ours(args):
         act_bytes = 2
     # algorithmic, layer-granular bytes per launch: conv1 2A, conv10 A+B, conv2+res 3A+B
     # executed useful FLOPs per launch (the base/frame split of conv2 halves its K on the tensor-core path)
-    kinds = {
-        "conv1_3x3": {"bytes": 2 * A_el * act_bytes, "flops": 2.0 * clips * 7 * hw * 64 * 576},
-        "conv2_3x3": {"bytes": 3 * A_el * act_bytes + B_el * 4,   # partial sums / base are fp32 (or fp32-sized)
-                      "flops": 2.0 * clips * 7 * hw * 64 * (576 if tc else 1152)},
-        "conv10_1x1": {"bytes": (A_el + B_el) * act_bytes, "flops": 2.0 * clips * hw * 64 * 448},
-    }
+    f_conv1 = 2.0 * clips * 7 * hw * 64 * 576
+    f_conv10 = 2.0 * clips * hw * 64 * 448
+    f_pbase = 2.0 * clips * hw * 64 * 576
+    if tc:
+        # tensor-core path: two persistent launches per block -
+        #   "conv1_3x3" = conv1 + conv10 (2A + A + B), "conv2_3x3" = base-half partial sums + frame half (+ residual)
+        kinds = {
+            "conv1_3x3": {"bytes": (3 * A_el + B_el) * act_bytes, "flops": f_conv1 + f_conv10},
+            "conv2_3x3": {"bytes": (3 * A_el + B_el) * act_bytes + 2 * B_el * 4, "flops": f_conv1 + f_pbase},
+        }
+    else:
+        kinds = {
+            "conv1_3x3": {"bytes": 2 * A_el * act_bytes, "flops": f_conv1},
+            "conv2_3x3": {"bytes": (3 * A_el + B_el) * act_bytes, "flops": 2.0 * clips * 7 * hw * 64 * 1152},
+            "conv10_1x1": {"bytes": (A_el + B_el) * act_bytes, "flops": f_conv10},
+        }
     prof_total = sum(v[0] for v in prof.values())
     shares = {k: (v[0] / prof_total if prof_total > 0 else 0.0) for k, v in prof.items()}
     dom = max(kinds, key=lambda k: prof[k][0])

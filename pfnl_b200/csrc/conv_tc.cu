@@ -3,29 +3,37 @@
 //
 // Data layout in HBM: activations are fp16 NHWC planes [images, H, W, 64] (one pixel = one
 // 128-byte row = one 128B-swizzle row).  PFNL_PREC_TC_FP16 keeps one plane per tensor;
-// PFNL_PREC_TC_FP16X3 keeps two (hi = fp16(v), lo = fp16((v-hi)*2048)) and runs three MMAs per
-// k-step (hi*hi into D0; hi*lo' + lo'*hi into D1; result D0 + D1/2048), which carries ~22
-// mantissa bits through the fp16 tensor pipe.  TMEM accumulation truncates (measured by
-// probes/umma_probe.cu), so in the x3 mode D0 is split into NCH accumulation chains (one per
-// kernel row) that are summed round-to-nearest in the epilogue: fewer truncating adds per chain.
+// PFNL_PREC_TC_FP16X3 keeps two (hi = fp16(v), lo = fp16((v-hi)*2048)) and computes
+//   [D0 | D1] += A_hi x [W_hi ; W_lo]   (one N = 128 MMA per k-step: one A read for two products)
+//        D1   += A_lo x  W_hi           (N = 64)
+// result D0 + D1/2048: ~22 mantissa bits through the fp16 tensor pipe.  TMEM accumulation
+// truncates (probes/umma_probe.cu), so the 36 k-steps of a 3x3 tile are split into 2 accumulation
+// chains that the epilogue sums round-to-nearest.
 //
 // Implicit GEMM: M = 128 output pixels (a 16-row x 8-column spatial tile of one image),
 // N = 64 (48 for convmerge1) output channels, K = taps x 64 input channels.  Per tile ONE TMA
 // box {64 ch, 10 px, 18 rows} (out-of-bounds zero fill == 'same' zero padding) lands a halo
 // patch in smem; the A operand of tap (dy,dx) is the same patch addressed through a UMMA
 // descriptor whose start is shifted by (dy*10+dx) 128-byte rows and whose 8-row-group stride
-// (SBO) is 10*128 - so each input byte is fetched from L2 once per tile, not 9 times.  (The
-// 128B swizzle is a function of the absolute smem address on B200, so shifted windows need no
-// padding and base_offset = 0; probes/umma_probe.cu.)
-// Weights ([taps][N][64] fp16, pre-swizzled) stay resident in smem for the CTA's lifetime.
+// (SBO) is 10*128 - each input byte is fetched from L2 once per tile, not 9 times.  (The 128B
+// swizzle is a function of the absolute smem address on B200: shifted windows need no padding and
+// base_offset = 0, and they run at the same MMA rate as standard tiles; probes/.)
+// Weights ([taps][N][64] fp16, pre-swizzled) are resident in smem while a phase runs.
 //
-// Warp roles (576 threads, 1 CTA / SM, persistent over tiles): warp 0 = TMA producer, warp 1 =
-// MMA issuer (converged warp, one elected lane issues), warps 2-17 = epilogue (tcgen05.ld -> bias /
-// leaky_relu / partial sums / residual -> fp16 planes or fp32; 16 warps so that conversion/ALU
-// latency is hidden - with 4 warps the epilogue, not the MMAs, set the tile time).  TMEM accumulators are double
-// buffered so the epilogue of tile i overlaps the MMAs of tile i+1.  Launched with programmatic
-// dependent launch: the prologue (barriers, TMEM alloc, weight load) overlaps the previous
-// kernel's tail; griddepcontrol.wait guards every access to activations.
+// One launch runs up to two PHASES back to back on the same persistent CTAs, swapping the weight
+// image in smem between them:   conv1 -> conv10   and   conv2(base half, fp32 partial) -> conv2(frame half).
+// A work unit is one spatial tile x 7 frames, and a CTA owns the same units in both phases, so the
+// phase-2 inputs that phase 1 produced are the CTA's own writes (conv10 reads the 7 conv1 tiles of
+// its unit; the frame half adds the partial sums its own threads stored).  This halves the launch
+// count of the PFRB stack: the 128-tile conv10 / partial-sum kernels were dominated by launch gap,
+// weight load and first-load latency, not by their MMAs.
+//
+// Warp roles (576 threads, 1 CTA / SM, persistent): warp 0 = TMA producer, warp 1 = MMA issuer
+// (converged warp, one elected lane issues; descriptors advance by constant adds), warps 2-17 =
+// epilogue (16 warps: 4 TMEM lane quarters x 4 sixteen-channel chunks; tcgen05.ld -> bias /
+// leaky_relu / partial sums / residual -> fp16 planes or fp32, 256-bit global accesses, operands
+// prefetched before the accumulator wait).  TMEM accumulators are double buffered.  Programmatic
+// dependent launch overlaps the prologue with the previous kernel's tail.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -45,53 +53,63 @@ enum TcEpi {
   kEpiFinalF32 = 3     // v = lrelu(acc + previous + bias)             -> fp32
 };
 
-struct TcConvParams {
-  int H, W, tiles_x, tiles_y, n_tiles;
-  int frames, n_units;   // work unit = one spatial tile x `frames` consecutive output images (7 when the
-                         // output is per-frame: the CTA keeps the unit's shared partial sums in registers)
-  int img_mul, img_add;  // source image coordinate of stage s = out_img*img_mul + img_add + s
+struct TcPhase {
+  CUtensorMap tm_hi, tm_lo;  // source planes
+  const __half* wimg;        // weight image of this phase
+  int frames, n_units;       // unit = one spatial tile x `frames` consecutive output images
+  int img_mul, img_add;      // source image coordinate of stage s = out_img*img_mul + img_add + s
   int epi;
-  int accumulate;        // kEpiPartialF32: add the previous content of out_f32
-  int pb_div;            // pbase image index = out_img / pb_div
-  const float* bias;     // [NOUT]
-  const float* pbase;    // fp32 [out_img/pb_div][H][W][64]
+  int accumulate;            // kEpiPartialF32: add the previous content of out_f32
+  const float* bias;         // [NOUT] or NULL
+  const float* pbase;        // fp32 [out_img/frames][H][W][64] (kEpiResPlanes)
   __half* out_hi;
   __half* out_lo;
   const __half* res_hi;
   const __half* res_lo;
-  float* out_f32;        // [out_images][H][W][NOUT]
-  long long* trace;      // debug (PFNL_TC_TRACE=1): clock64 stamps of CTA 0, [role][event] ; else NULL
+  float* out_f32;            // [out_images][H][W][NOUT]
 };
 
-// trace slots: role 0 producer, 1 MMA issuer, 2 epilogue warp 2; 64 events per role
-#define TC_TRACE(role, ev)                                                                  \
-  do {                                                                                      \
-    if (p.trace != nullptr && blockIdx.x == 0 && (ev) < 64) p.trace[(role) * 64 + (ev)] = clock64(); \
+struct TcCommon {
+  int H, W, tiles_x, tiles_y;
+  int nphases;
+  int phase1_reads_phase0;  // phase 1 TMA-loads tensors that phase 0 of the same CTA wrote (conv1 -> conv10)
+  long long* trace;  // debug (PFNL_TC_TRACE=1): clock64 stamps of CTA 0, [role][event]; else NULL
+};
+
+#define TC_TRACE(role, ev)                                                                              \
+  do {                                                                                                  \
+    if (cm.trace != nullptr && blockIdx.x == 0 && (ev) < 64) cm.trace[(role) * 64 + (ev)] = clock64(); \
   } while (0)
 
-template <int KS, int NSRC, int NSPLIT, int NOUT, int NCH>
-struct TcCfg {
+// compile-time description of one phase
+template <int KS_, int NSRC_, int NOUT_, int NCH_>
+struct PhaseCfg {
+  static constexpr int KS = KS_, NSRC = NSRC_, NOUT = NOUT_, NCH = NCH_;
   static constexpr int TAPS = KS * KS;
   static constexpr int NTAPS = NSRC * TAPS;
   static constexpr int BOX_W = KS == 3 ? kTcPatchW3 : 8;
   static constexpr int BOX_H = KS == 3 ? 18 : 16;
   static constexpr int PATCH_BYTES = BOX_W * BOX_H * 128;
-  static constexpr int SLOT_BYTES = (PATCH_BYTES + 1023) / 1024 * 1024;
-  static constexpr int WT_BYTES = NOUT * 128;            // one plane of one tap: [NOUT rows][64 ci]
-  static constexpr int TAP_BYTES = NSPLIT * WT_BYTES;    // split mode: [W_hi ; W_lo] stacked -> one N = 2*NOUT tile
-  static constexpr int W_BYTES = NTAPS * TAP_BYTES;
+  static constexpr int WT_BYTES = NOUT * 128;  // one plane of one tap: [NOUT rows][64 ci]
+};
+
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+
+template <class P0, class P1, int NSPLIT>
+struct KernelCfg {
+  static constexpr int TAP0 = NSPLIT * P0::WT_BYTES, TAP1 = NSPLIT * P1::WT_BYTES;  // [W_hi ; W_lo] stacked
+  static constexpr int W0 = P0::NTAPS * TAP0, W1 = P1::NTAPS * TAP1;
+  static constexpr int W_BYTES = cmax(W0, W1);
+  static constexpr int SLOT_BYTES = (cmax(P0::PATCH_BYTES, P1::PATCH_BYTES) + 1023) / 1024 * 1024;
   static constexpr int SMEM_MAX = 227 * 1024;
   static constexpr int CTRL_BYTES = 1024;
-  static constexpr int BUDGET = SMEM_MAX - 1024 /*align slack*/ - CTRL_BYTES - W_BYTES;
-  static constexpr int TOTAL_SLOTS = BUDGET / SLOT_BYTES;
-  // ONE ring of patch slots shared by the hi and lo planes (loads alternate lo, hi, lo, hi ...):
-  // with 3 slots every TMA load is issued >= one full plane pass (1.7-3.5 K cycles) before the
-  // MMAs need it, which hides the ~2 us (4 K cycle) load latency seen under full-chip load.
+  static constexpr int TOTAL_SLOTS = (SMEM_MAX - 1024 - CTRL_BYTES - W_BYTES) / SLOT_BYTES;
+  // ONE ring of patch slots shared by the hi and lo planes (loads alternate hi, lo, hi, lo ...)
   static constexpr int NS = TOTAL_SLOTS > 6 ? 6 : TOTAL_SLOTS;
   static constexpr int SMEM_BYTES = 1024 + CTRL_BYTES + W_BYTES + NS * SLOT_BYTES;
   // TMEM per accumulator buffer: NCH chains; a chain is [D0 (NOUT cols) | D1 (NOUT cols, split mode)]
   static constexpr int CH_STRIDE = NSPLIT == 2 ? 128 : 64;
-  static constexpr int TMEM_BUF_COLS = NCH * CH_STRIDE;
+  static constexpr int TMEM_BUF_COLS = cmax(P0::NCH, P1::NCH) * CH_STRIDE;
   static constexpr int TMEM_NEED = 2 * TMEM_BUF_COLS;
   static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
   static_assert(TMEM_NEED <= 512, "TMEM overflow");
@@ -99,16 +117,23 @@ struct TcCfg {
   static_assert(SMEM_BYTES <= SMEM_MAX, "shared memory overflow");
 };
 
-constexpr int kPrefetchAhead = 2;                  // tiles of L2 prefetch distance in the TMA producer
-constexpr int kTcEpiWarps = 16;                    // 4 TMEM lane quarters x 4 sixteen-channel chunks
+constexpr int kPrefetchAhead = 2;                   // tiles of L2 prefetch distance in the TMA producer
+constexpr int kTcEpiWarps = 16;                     // 4 TMEM lane quarters x 4 sixteen-channel chunks
 constexpr int kTcThreads = (2 + kTcEpiWarps) * 32;  // + producer warp + MMA warp = 576
 
 struct TcCtrl {
-  uint64_t wfull;
+  uint64_t wfull;        // weight image of the current phase has landed
+  uint64_t wfree;        // all MMAs of the finished phase are complete (weights may be overwritten)
+  uint64_t stores_done;  // all epilogue stores of the finished phase are globally visible
+  uint64_t peers_ready;  // every CTA of the cluster has finished phase 0 (weights may be multicast over)
   uint64_t full[8], empty[8];
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
-  float bias[64];
+  float bias[2][64];
+};
+
+struct TcRing {  // ring slot cursor (producer and MMA issuer keep identical copies)
+  int sl, ph;
 };
 
 __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
@@ -116,8 +141,7 @@ __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
   lo = __float2half_rn((v - __half2float(hi)) * 2048.f);
 }
 
-// accumulation chain of tap tp (3x3: taps 0-4 -> chain 0, 5-8 -> chain 1 when NCH = 2; one chain per
-// kernel row when NCH = 3) or of source s (1x1 over 7 sources)
+// accumulation chain of tap tp (3x3: taps 0-4 -> chain 0, 5-8 -> chain 1 when NCH = 2) or source s
 template <int KS, int NCH>
 __device__ __forceinline__ constexpr int tc_chain(int tp, int s) {
   return NCH == 1 ? 0 : (KS == 3 ? (NCH == 2 ? (tp >= 5 ? 1 : 0) : tp / 3) : s % NCH);
@@ -151,226 +175,179 @@ __device__ __forceinline__ void st256(void* ptr, const U256& r) {
                "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]), "r"(r.w[7])
                : "memory");
 }
-
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-template <int KS, int NSRC, int NSPLIT, int NOUT, int NCH>
-__global__ void __launch_bounds__(kTcThreads, 1)
-    conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-                   const __half* __restrict__ wimg, const TcConvParams p) {
-  using C = TcCfg<KS, NSRC, NSPLIT, NOUT, NCH>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* wsm = smem;                                  // [NSPLIT][NTAPS][WT_BYTES]
-  uint8_t* ring = wsm + C::W_BYTES;                     // [NS][SLOT_BYTES]
-  TcCtrl* ctl = reinterpret_cast<TcCtrl*>(ring + C::NS * C::SLOT_BYTES);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int PAD = (KS - 1) / 2;
+// This CTA's share (1/cs) of a weight image: bulk copy L2 -> smem, multicast to every CTA of the cluster.
+template <int W_BYTES>
+__device__ __forceinline__ void load_weights_slice(uint8_t* wsm, const __half* wimg, uint64_t* wfull, uint32_t cs,
+                                                   uint32_t cr) {
+  const int slice = W_BYTES / (int)cs;  // W_BYTES is a multiple of 4 * 1024
+  const int beg = (int)cr * slice;
+  for (int off = beg; off < beg + slice; off += 32768) {
+    const int n = (beg + slice - off) < 32768 ? (beg + slice - off) : 32768;
+    if (cs > 1)
+      bulk_load_multicast(wsm + off, reinterpret_cast<const uint8_t*>(wimg) + off, n, wfull,
+                          (uint16_t)((1u << cs) - 1));
+    else
+      bulk_load(wsm + off, reinterpret_cast<const uint8_t*>(wimg) + off, n, wfull);
+  }
+}
 
-  // ---- prologue: touches only weights / bias (never written by any kernel), overlaps the previous
-  //      kernel's tail under programmatic dependent launch
-  if (tid == 0) {
-    mbar_init(&ctl->wfull, 1);
-    for (int i = 0; i < 8; ++i) {
-      mbar_init(&ctl->full[i], 1);
-      mbar_init(&ctl->empty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&ctl->tmem_full[i], 1);
-      mbar_init(&ctl->tmem_empty[i], kTcEpiWarps);
-    }
-    fence_mbar_init();
-    fence_proxy_async();
-    tma_prefetch_desc(&tm_hi);
-    if (NSPLIT == 2) tma_prefetch_desc(&tm_lo);
-    mbar_arrive_expect_tx(&ctl->wfull, C::W_BYTES);  // this CTA receives the whole image
-  }
-  if (tid < 64) ctl->bias[tid] = (p.bias != nullptr && tid < NOUT) ? p.bias[tid] : 0.f;
-  if (warp == 1) {
-    tmem_alloc(&ctl->tmem_base, C::TMEM_COLS);
-    tmem_relinquish();
-  }
-  // Weights: every CTA of the cluster fetches 1/cs of the image from L2 and TMA-multicasts it into
-  // all cs CTAs (same smem offset, same mbarrier offset) - L2->SM weight traffic drops cs-fold.
-  const uint32_t cs = cluster_nctarank(), cr = cluster_ctarank();
-  if (cs > 1) cluster_sync_all();  // every peer's wfull barrier is initialised and armed
-  if (tid == 0) {
-    const int slice = C::W_BYTES / (int)cs;  // W_BYTES is a multiple of 1024*4
-    const int beg = (int)cr * slice;
-    for (int off = beg; off < beg + slice; off += 32768) {
-      const int n = (beg + slice - off) < 32768 ? (beg + slice - off) : 32768;
-      if (cs > 1)
-        bulk_load_multicast(wsm + off, reinterpret_cast<const uint8_t*>(wimg) + off, n, &ctl->wfull,
-                            (uint16_t)((1u << cs) - 1));
-      else
-        bulk_load(wsm + off, reinterpret_cast<const uint8_t*>(wimg) + off, n, &ctl->wfull);
-    }
-  }
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem = ctl->tmem_base;
-  pdl_launch_dependents();  // let the next kernel's CTAs start their prologue as SMs free up
-  pdl_wait();               // activations written by the previous kernel are visible after this
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int sl = 0, ph = 0, tcount = 0;
-      TC_TRACE(0, 0);
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x)
-      for (int t = 0; t < p.frames; ++t, ++tcount) {
-        const int tx = u % p.tiles_x;
-        const int r = u / p.tiles_x;
-        const int ty = r % p.tiles_y;
-        const int img = (r / p.tiles_y) * p.frames + t;
-        const int x0 = tx * 8 - PAD, y0 = ty * 16 - PAD;
-        // L2 prefetch, kPrefetchAhead tiles ahead: the smem ring is only 3 slots deep in the split
-        // mode (147 KB of resident weights), not enough to cover DRAM latency under full-chip load
-        {
-          int ft = t + kPrefetchAhead, fu = u;
-          while (ft >= p.frames) {
-            ft -= p.frames;
-            fu += gridDim.x;
-          }
-          if (fu < p.n_units) {
-            const int ftx = fu % p.tiles_x;
-            const int fr = fu / p.tiles_x;
-            const int fty = fr % p.tiles_y;
-            const int fimg = (fr / p.tiles_y) * p.frames + ft;
-            for (int s = 0; s < NSRC; ++s) {
-              const int fic = fimg * p.img_mul + p.img_add + s;
-              tma_prefetch_4d(&tm_hi, 0, ftx * 8 - PAD, fty * 16 - PAD, fic);
-              if (NSPLIT == 2) tma_prefetch_4d(&tm_lo, 0, ftx * 8 - PAD, fty * 16 - PAD, fic);
-            }
+// ---------------------------------------------------------------------------------------------------------
+// role bodies, one call per phase
+// ---------------------------------------------------------------------------------------------------------
+template <class PC, class KC, int NSPLIT>
+__device__ __forceinline__ void producer_phase(const TcPhase& P, const TcCommon& cm, uint8_t* ring, TcCtrl* ctl,
+                                               TcRing& rg, int& tcount) {
+  constexpr int PAD = (PC::KS - 1) / 2;
+  for (int u = blockIdx.x; u < P.n_units; u += gridDim.x)
+    for (int t = 0; t < P.frames; ++t, ++tcount) {
+      const int tx = u % cm.tiles_x;
+      const int r = u / cm.tiles_x;
+      const int ty = r % cm.tiles_y;
+      const int img = (r / cm.tiles_y) * P.frames + t;
+      const int x0 = tx * 8 - PAD, y0 = ty * 16 - PAD;
+      {  // L2 prefetch kPrefetchAhead tiles ahead
+        int ft = t + kPrefetchAhead, fu = u;
+        while (ft >= P.frames) {
+          ft -= P.frames;
+          fu += gridDim.x;
+        }
+        if (fu < P.n_units) {
+          const int ftx = fu % cm.tiles_x;
+          const int fr = fu / cm.tiles_x;
+          const int fty = fr % cm.tiles_y;
+          const int fimg = (fr / cm.tiles_y) * P.frames + ft;
+          for (int s = 0; s < PC::NSRC; ++s) {
+            const int fic = fimg * P.img_mul + P.img_add + s;
+            tma_prefetch_4d(&P.tm_hi, 0, ftx * 8 - PAD, fty * 16 - PAD, fic);
+            if (NSPLIT == 2) tma_prefetch_4d(&P.tm_lo, 0, ftx * 8 - PAD, fty * 16 - PAD, fic);
           }
         }
-        for (int s = 0; s < NSRC; ++s) {
-          const int ic = img * p.img_mul + p.img_add + s;
-#pragma unroll
-          for (int pl = 0; pl < NSPLIT; ++pl) {  // hi plane first (consumed first), then lo
-            mbar_wait(&ctl->empty[sl], ph ^ 1);
-            mbar_arrive_expect_tx(&ctl->full[sl], C::PATCH_BYTES);
-            tma_load_4d(ring + sl * C::SLOT_BYTES, pl == 1 ? &tm_lo : &tm_hi, &ctl->full[sl], 0, x0, y0, ic);
-            if (++sl == C::NS) {
-              sl = 0;
-              ph ^= 1;
-            }
-          }
-        }
-        TC_TRACE(0, 1 + tcount);
       }
+      for (int s = 0; s < PC::NSRC; ++s) {
+        const int ic = img * P.img_mul + P.img_add + s;
+#pragma unroll
+        for (int pl = 0; pl < NSPLIT; ++pl) {  // hi plane first (consumed first), then lo
+          mbar_wait(&ctl->empty[rg.sl], rg.ph ^ 1);
+          mbar_arrive_expect_tx(&ctl->full[rg.sl], PC::PATCH_BYTES);
+          tma_load_4d(ring + rg.sl * KC::SLOT_BYTES, pl == 1 ? &P.tm_lo : &P.tm_hi, &ctl->full[rg.sl], 0, x0, y0, ic);
+          if (++rg.sl == KC::NS) {
+            rg.sl = 0;
+            rg.ph ^= 1;
+          }
+        }
+      }
+      TC_TRACE(0, 1 + tcount);
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    // The whole warp walks the loop converged (waits are warp-uniform); one elected lane issues.
-    // Descriptors are advanced by adding compile-time constants to a per-slot base descriptor:
-    // ~3 instructions per tcgen05.mma instead of rebuilding two descriptors each time.
-    constexpr uint32_t idesc_lo = make_idesc_f16(128, NOUT);           // A_lo x W_hi          -> D1
-    constexpr uint32_t idesc_hi = make_idesc_f16(128, NSPLIT * NOUT);  // A_hi x [W_hi ; W_lo] -> [D0 | D1]
-    constexpr uint32_t SBO_A = C::BOX_W * 128;
-    const uint64_t wd = make_sdesc_sw128(smem_u32(wsm), 1024, 0);
-    mbar_wait(&ctl->wfull, 0);
-    fence_after_sync();
-    if (lane == 0) TC_TRACE(1, 0);
-    int sl = 0, ph = 0, it = 0;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x)
-    for (int t = 0; t < p.frames; ++t, ++it) {
+}
+
+template <class PC, class KC, int NSPLIT>
+__device__ __forceinline__ void mma_phase(const TcPhase& P, const TcCommon& cm, uint8_t* wsm, uint8_t* ring,
+                                          TcCtrl* ctl, uint32_t tmem, TcRing& rg, int& it, int lane) {
+  constexpr int KS = PC::KS, NSRC = PC::NSRC, NOUT = PC::NOUT, NCH = PC::NCH, TAPS = PC::TAPS;
+  constexpr int TAP_BYTES = NSPLIT * PC::WT_BYTES;
+  constexpr uint32_t idesc_lo = make_idesc_f16(128, NOUT);           // A_lo x W_hi          -> D1
+  constexpr uint32_t idesc_hi = make_idesc_f16(128, NSPLIT * NOUT);  // A_hi x [W_hi ; W_lo] -> [D0 | D1]
+  constexpr uint32_t SBO_A = PC::BOX_W * 128;
+  const uint64_t wd = make_sdesc_sw128(smem_u32(wsm), 1024, 0);
+  for (int u = blockIdx.x; u < P.n_units; u += gridDim.x)
+    for (int t = 0; t < P.frames; ++t, ++it) {
       const int buf = it & 1;
       mbar_wait(&ctl->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
       fence_after_sync();
-      const uint32_t dbase = tmem + buf * C::TMEM_BUF_COLS;
+      const uint32_t dbase = tmem + buf * KC::TMEM_BUF_COLS;
       uint32_t accmask = 0;  // bit c: chain c's block [D0|D1] has been written in this tile
       for (int s = 0; s < NSRC; ++s) {
-        const uint64_t wsd = wd + (uint64_t)((s * C::TAPS * C::TAP_BYTES) >> 4);
-        // ---- hi-plane pass: [D0_c | D1_c] (+)= A_hi x [W_hi ; W_lo]   (one N = 2*NOUT MMA per k-step)
-        mbar_wait(&ctl->full[sl], ph);
+        const uint64_t wsd = wd + (uint64_t)((s * TAPS * TAP_BYTES) >> 4);
+        // ---- hi-plane pass: [D0_c | D1_c] (+)= A_hi x [W_hi ; W_lo]
+        mbar_wait(&ctl->full[rg.sl], rg.ph);
         fence_after_sync();
         if (lane == 0 && s == 0) TC_TRACE(1, 1 + 2 * it);
         {
-          const uint64_t ad = make_sdesc_sw128(smem_u32(ring + sl * C::SLOT_BYTES), SBO_A, 0);
+          const uint64_t ad = make_sdesc_sw128(smem_u32(ring + rg.sl * KC::SLOT_BYTES), SBO_A, 0);
           if (elect_one()) {
             uint32_t am = accmask;
 #pragma unroll
-            for (int tp = 0; tp < C::TAPS; ++tp) {
+            for (int tp = 0; tp < TAPS; ++tp) {
               const int ch = tc_chain<KS, NCH>(tp, s);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint32_t aoff = (((tp / KS) * C::BOX_W + (tp % KS)) * 128 + k * 32) >> 4;
-                const uint32_t boff = (tp * C::TAP_BYTES + k * 32) >> 4;
-                mma_f16(dbase + ch * C::CH_STRIDE, ad + aoff, wsd + boff, idesc_hi, (am >> ch) & 1u);
+                const uint32_t aoff = (((tp / KS) * PC::BOX_W + (tp % KS)) * 128 + k * 32) >> 4;
+                const uint32_t boff = (tp * TAP_BYTES + k * 32) >> 4;
+                mma_f16(dbase + ch * KC::CH_STRIDE, ad + aoff, wsd + boff, idesc_hi, (am >> ch) & 1u);
                 am |= 1u << ch;
               }
             }
-            mma_commit(&ctl->empty[sl]);
+            mma_commit(&ctl->empty[rg.sl]);
             if (NSPLIT == 1 && s == NSRC - 1) mma_commit(&ctl->tmem_full[buf]);
           }
           __syncwarp();
 #pragma unroll
-          for (int tp = 0; tp < C::TAPS; ++tp) accmask |= 1u << tc_chain<KS, NCH>(tp, s);
-          if (++sl == C::NS) {
-            sl = 0;
-            ph ^= 1;
+          for (int tp = 0; tp < TAPS; ++tp) accmask |= 1u << tc_chain<KS, NCH>(tp, s);
+          if (++rg.sl == KC::NS) {
+            rg.sl = 0;
+            rg.ph ^= 1;
           }
         }
         if (NSPLIT == 2) {
           // ---- lo-plane pass: D1 of chain 0 += A_lo x W_hi (chain 0 was initialised by the hi pass:
           //      tap 0 / source 0 always belongs to chain 0), so this always accumulates
-          mbar_wait(&ctl->full[sl], ph);
+          mbar_wait(&ctl->full[rg.sl], rg.ph);
           fence_after_sync();
-          const uint64_t ad = make_sdesc_sw128(smem_u32(ring + sl * C::SLOT_BYTES), SBO_A, 0);
+          const uint64_t ad = make_sdesc_sw128(smem_u32(ring + rg.sl * KC::SLOT_BYTES), SBO_A, 0);
           if (elect_one()) {
 #pragma unroll
-            for (int tp = 0; tp < C::TAPS; ++tp) {
+            for (int tp = 0; tp < TAPS; ++tp) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint32_t aoff = (((tp / KS) * C::BOX_W + (tp % KS)) * 128 + k * 32) >> 4;
-                const uint32_t boff = (tp * C::TAP_BYTES + k * 32) >> 4;
+                const uint32_t aoff = (((tp / KS) * PC::BOX_W + (tp % KS)) * 128 + k * 32) >> 4;
+                const uint32_t boff = (tp * TAP_BYTES + k * 32) >> 4;
                 mma_f16(dbase + NOUT, ad + aoff, wsd + boff, idesc_lo, 1u);
               }
             }
-            mma_commit(&ctl->empty[sl]);
+            mma_commit(&ctl->empty[rg.sl]);
             if (s == NSRC - 1) mma_commit(&ctl->tmem_full[buf]);  // same thread that issued the MMAs
           }
           __syncwarp();
-          if (++sl == C::NS) {
-            sl = 0;
-            ph ^= 1;
+          if (++rg.sl == KC::NS) {
+            rg.sl = 0;
+            rg.ph ^= 1;
           }
         }
         if (lane == 0 && s == NSRC - 1) TC_TRACE(1, 2 + 2 * it);
       }
     }
-  } else {
-    // ===================== epilogue (warps 2..17) =====================
-    // 16 warps (4 per SM sub-partition, so ALU / conversion latency is hidden): warp -> TMEM lane
-    // quarter (warp & 3, a hardware restriction) x one 16-channel chunk ((warp-2) >> 2).  Operands
-    // that do not depend on the accumulator (fp32 partial sums, residual planes, previous fp32
-    // content) are loaded BEFORE waiting for the MMAs, so their latency hides under the tile's MMAs.
-    const int q = warp & 3;
-    const int c0 = ((warp - 2) >> 2) * 16;
-    const bool chunk_active = c0 < NOUT;
-    const int m = q * 32 + lane;        // row of the tile = TMEM lane
-    const int my = m >> 3, mx = m & 7;  // pixel inside the 16x8 tile
-    const bool epi_planes = p.epi == kEpiActPlanes || p.epi == kEpiResPlanes;
-    const bool epi_res = p.epi == kEpiResPlanes;
-    const bool epi_prev = (p.epi == kEpiPartialF32 && p.accumulate) || p.epi == kEpiFinalF32;
-    int it = 0;
-    U256 pre[2];  // 16 fp32: partial sums (kept across the unit's frames) or previous fp32 content
+}
+
+template <class PC, class KC, int NSPLIT>
+__device__ __forceinline__ void epilogue_phase(const TcPhase& P, const TcCommon& cm, TcCtrl* ctl, const float* bias_sm,
+                                               uint32_t tmem, int& it, int warp, int lane) {
+  constexpr int NOUT = PC::NOUT, NCH = PC::NCH;
+  const int q = warp & 3;             // TMEM lane quarter this warp may access (hardware restriction)
+  const int c0 = ((warp - 2) >> 2) * 16;
+  const bool chunk_active = c0 < NOUT;
+  const int m = q * 32 + lane;        // row of the tile = TMEM lane
+  const int my = m >> 3, mx = m & 7;  // pixel inside the 16x8 tile
+  const bool epi_planes = P.epi == kEpiActPlanes || P.epi == kEpiResPlanes;
+  const bool epi_res = P.epi == kEpiResPlanes;
+  const bool epi_prev = (P.epi == kEpiPartialF32 && P.accumulate) || P.epi == kEpiFinalF32;
+  U256 pre[2];  // 16 fp32: partial sums (kept across the unit's frames) or previous fp32 content
 #pragma unroll
-    for (int j = 0; j < 8; ++j) pre[0].w[j] = pre[1].w[j] = 0u;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x)
-    for (int t = 0; t < p.frames; ++t, ++it) {
+  for (int j = 0; j < 8; ++j) pre[0].w[j] = pre[1].w[j] = 0u;
+  for (int u = blockIdx.x; u < P.n_units; u += gridDim.x)
+    for (int t = 0; t < P.frames; ++t, ++it) {
       const int buf = it & 1;
-      const int tx = u % p.tiles_x;
-      const int r = u / p.tiles_x;
-      const int ty = r % p.tiles_y;
-      const int nimg = r / p.tiles_y;
-      const int img = nimg * p.frames + t;
+      const int tx = u % cm.tiles_x;
+      const int r = u / cm.tiles_x;
+      const int ty = r % cm.tiles_y;
+      const int nimg = r / cm.tiles_y;
+      const int img = nimg * P.frames + t;
       const int y = ty * 16 + my, x = tx * 8 + mx;
-      const bool inb = chunk_active && y < p.H && x < p.W;
-      const long long pix = ((long long)img * p.H + y) * p.W + x;
+      const bool inb = chunk_active && y < cm.H && x < cm.W;
+      const long long pix = ((long long)img * cm.H + y) * cm.W + x;
       // ---- prefetch (independent of the accumulator) ----
       U256 rh, rl;
 #pragma unroll
@@ -378,14 +355,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       if (inb) {
         if (epi_res) {
           if (t == 0) {  // the base-half partial sums are shared by the unit's 7 frames: load once
-            const float* pb = p.pbase + (((long long)nimg * p.H + y) * p.W + x) * 64 + c0;
+            const float* pb = P.pbase + (((long long)nimg * cm.H + y) * cm.W + x) * 64 + c0;
             pre[0] = ld256(pb);
             pre[1] = ld256(pb + 8);
           }
-          rh = ld256(p.res_hi + pix * 64 + c0);
-          if (NSPLIT == 2) rl = ld256(p.res_lo + pix * 64 + c0);
+          rh = ld256(P.res_hi + pix * 64 + c0);
+          if (NSPLIT == 2) rl = ld256(P.res_lo + pix * 64 + c0);
         } else if (epi_prev) {
-          const float* o = p.out_f32 + pix * NOUT + c0;
+          const float* o = P.out_f32 + pix * NOUT + c0;
           pre[0] = ld256(o);
           pre[1] = ld256(o + 8);
         }
@@ -397,12 +374,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       if (chunk_active) {
         // chain c: D0 at c*CH_STRIDE, D1 (split mode) at c*CH_STRIDE + NOUT.  Chains are summed in
         // fp32 round-to-nearest here; D1 carries the 2^-11-scaled cross terms.
-        const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + buf * C::TMEM_BUF_COLS + c0;
+        const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + buf * KC::TMEM_BUF_COLS + c0;
         uint32_t d0[NCH][16], d1[NSPLIT == 2 ? NCH : 1][16];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          tmem_ld_32x32b_x16(t0 + c * C::CH_STRIDE, d0[c]);
-          if (NSPLIT == 2) tmem_ld_32x32b_x16(t0 + c * C::CH_STRIDE + NOUT, d1[c]);
+          tmem_ld_32x32b_x16(t0 + c * KC::CH_STRIDE, d0[c]);
+          if (NSPLIT == 2) tmem_ld_32x32b_x16(t0 + c * KC::CH_STRIDE + NOUT, d1[c]);
         }
         tmem_ld_wait();
 #pragma unroll
@@ -431,7 +408,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
         if (epi_planes) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = lrelu(v[j] + ctl->bias[c0 + j]);
+          for (int j = 0; j < 16; ++j) v[j] = lrelu(v[j] + bias_sm[c0 + j]);
           if (epi_res) {
             const __half* hh = reinterpret_cast<const __half*>(&rh);
             if (NSPLIT == 2) {
@@ -454,12 +431,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             else
               ph[j] = __float2half_rn(v[j]);
           }
-          st256(p.out_hi + pix * 64 + c0, oh);
-          if (NSPLIT == 2) st256(p.out_lo + pix * 64 + c0, ol);
+          st256(P.out_hi + pix * 64 + c0, oh);
+          if (NSPLIT == 2) st256(P.out_lo + pix * 64 + c0, ol);
         } else {
-          if (p.epi == kEpiFinalF32) {
+          if (P.epi == kEpiFinalF32) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = lrelu(v[j] + ctl->bias[c0 + j]);
+            for (int j = 0; j < 16; ++j) v[j] = lrelu(v[j] + bias_sm[c0 + j]);
           }
           U256 o0, o1;
 #pragma unroll
@@ -467,19 +444,137 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             o0.w[j] = __float_as_uint(v[j]);
             o1.w[j] = __float_as_uint(v[8 + j]);
           }
-          float* o = p.out_f32 + pix * NOUT + c0;
+          float* o = P.out_f32 + pix * NOUT + c0;
           st256(o, o0);
           st256(o + 8, o1);
         }
       }
       if (warp == 2 && lane == 0) TC_TRACE(2, 2 * it + 1);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <class P0, class P1, int NSPLIT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+    conv_tc_kernel(const __grid_constant__ TcPhase ph0, const __grid_constant__ TcPhase ph1, const TcCommon cm) {
+  using KC = KernelCfg<P0, P1, NSPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* wsm = smem;                 // weight image of the running phase
+  uint8_t* ring = wsm + KC::W_BYTES;   // [NS][SLOT_BYTES]
+  TcCtrl* ctl = reinterpret_cast<TcCtrl*>(ring + KC::NS * KC::SLOT_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- prologue: touches only weights / biases (never written by any kernel); overlaps the previous
+  //      kernel's tail under programmatic dependent launch
+  if (tid == 0) {
+    mbar_init(&ctl->wfull, 1);
+    mbar_init(&ctl->wfree, 1);
+    mbar_init(&ctl->stores_done, kTcEpiWarps);
+    mbar_init(&ctl->peers_ready, cluster_nctarank());
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&ctl->full[i], 1);
+      mbar_init(&ctl->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctl->tmem_full[i], 1);
+      mbar_init(&ctl->tmem_empty[i], kTcEpiWarps);
+    }
+    fence_mbar_init();
+    fence_proxy_async();
+    tma_prefetch_desc(&ph0.tm_hi);
+    if (NSPLIT == 2) tma_prefetch_desc(&ph0.tm_lo);
+    mbar_arrive_expect_tx(&ctl->wfull, KC::W0);  // this CTA receives the whole image
+    if (cm.nphases > 1) {  // warm L2 with the second phase's weight image (first touch is a DRAM read)
+      const int off = blockIdx.x * 16384;
+      if (off < KC::W1)
+        l2_prefetch_bulk(reinterpret_cast<const uint8_t*>(ph1.wimg) + off, (KC::W1 - off) < 16384 ? (KC::W1 - off) : 16384);
+    }
+  }
+  if (tid < 64) {
+    ctl->bias[0][tid] = (ph0.bias != nullptr && tid < P0::NOUT) ? ph0.bias[tid] : 0.f;
+    ctl->bias[1][tid] = (cm.nphases > 1 && ph1.bias != nullptr && tid < P1::NOUT) ? ph1.bias[tid] : 0.f;
+  }
+  if (warp == 1) {
+    tmem_alloc(&ctl->tmem_base, KC::TMEM_COLS);
+    tmem_relinquish();
+  }
+  // Weight images: each CTA of the cluster fetches 1/cs of the image from L2 and TMA-multicasts it
+  // into all cs CTAs (same smem offset, same mbarrier offset): L2->SM weight traffic drops cs-fold.
+  const uint32_t cs = cluster_nctarank(), cr = cluster_ctarank();
+  if (cs > 1) cluster_sync_all();  // every peer's barriers are initialised and wfull is armed
+  if (tid == 0) load_weights_slice<KC::W0>(wsm, ph0.wimg, &ctl->wfull, cs, cr);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = ctl->tmem_base;
+  pdl_launch_dependents();  // let the next kernel's CTAs start their prologue as SMs free up
+  pdl_wait();               // activations written by the previous kernel are visible after this
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      TcRing rg{0, 0};
+      int tcount = 0;
+      TC_TRACE(0, 0);
+      producer_phase<P0, KC, NSPLIT>(ph0, cm, ring, ctl, rg, tcount);
+      if (cm.nphases > 1) {
+        // swap the weight image once every MMA of phase 0 has completed, and make sure the phase-0
+        // outputs (written with generic-proxy stores by this CTA) are visible to the TMA (async proxy)
+        tma_prefetch_desc(&ph1.tm_hi);
+        if (NSPLIT == 2) tma_prefetch_desc(&ph1.tm_lo);
+        mbar_wait(&ctl->wfree, 0);
+        mbar_arrive_expect_tx(&ctl->wfull, KC::W1);
+        if (cs > 1) {
+          // peers may only overwrite my weights once I am done with phase 0 (and vice versa): tell every
+          // CTA of the cluster that I am ready, then wait until all of them are
+          for (uint32_t r = 0; r < cs; ++r) mbar_arrive_remote(&ctl->peers_ready, r);
+          mbar_wait_cluster(&ctl->peers_ready, 0);
+        }
+        load_weights_slice<KC::W1>(wsm, ph1.wimg, &ctl->wfull, cs, cr);  // needs only the MMAs to have drained
+        if (cm.phase1_reads_phase0) {
+          // phase-1 patches are this CTA's own phase-0 outputs (conv10 <- conv1): the generic-proxy
+          // stores must be visible to the TMA (async proxy) first
+          mbar_wait(&ctl->stores_done, 0);
+          fence_proxy_async_all();
+        }
+        producer_phase<P1, KC, NSPLIT>(ph1, cm, ring, ctl, rg, tcount);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (converged warp) =====================
+    TcRing rg{0, 0};
+    int it = 0;
+    mbar_wait(&ctl->wfull, 0);
+    fence_after_sync();
+    if (lane == 0) TC_TRACE(1, 0);
+    mma_phase<P0, KC, NSPLIT>(ph0, cm, wsm, ring, ctl, tmem, rg, it, lane);
+    if (cm.nphases > 1) {
+      if (elect_one()) mma_commit(&ctl->wfree);  // arrives when every MMA issued so far has completed
+      __syncwarp();
+      mbar_wait(&ctl->wfull, 1);
+      fence_after_sync();
+      mma_phase<P1, KC, NSPLIT>(ph1, cm, wsm, ring, ctl, tmem, rg, it, lane);
+    }
+  } else {
+    // ===================== epilogue (warps 2..17) =====================
+    int it = 0;
+    epilogue_phase<P0, KC, NSPLIT>(ph0, cm, ctl, ctl->bias[0], tmem, it, warp, lane);
+    if (cm.nphases > 1) {
+      if (cm.phase1_reads_phase0) {
+        // phase-0 stores of this thread -> visible device-wide and to the async proxy before phase 1 reads them
+        __threadfence();
+        fence_proxy_async_all();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->stores_done);
+      }
+      epilogue_phase<P1, KC, NSPLIT>(ph1, cm, ctl, ctl->bias[1], tmem, it, warp, lane);
+    }
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, C::TMEM_COLS);
-  // no CTA leaves while a peer's multicast may still target the cluster
-  if (cs > 1) cluster_sync_all();
+  if (warp == 1) tmem_dealloc(tmem, KC::TMEM_COLS);
+  if (cs > 1) cluster_sync_all();  // no CTA leaves while a peer's multicast may still target the cluster
 }
 
 // ---- weight images ------------------------------------------------------------------------------------
@@ -602,7 +697,6 @@ __global__ void __launch_bounds__(256, 2) conv0_planes_kernel(const float* __res
 namespace {
 
 int g_num_sms = 0;
-int g_chains = -1;
 bool g_pdl = true;
 
 bool pdl_enabled() {
@@ -610,38 +704,41 @@ bool pdl_enabled() {
   return g_pdl && !env_off;
 }
 
-// x3 mode: number of accumulation chains of the 3x3 kernels (2, or 1 with PFNL_TC_CHAINS=1)
-int x3_chains() {
-  if (g_chains < 0) {
-    const char* e = getenv("PFNL_TC_CHAINS");
-    g_chains = (e && atoi(e) == 1) ? 1 : 2;
-  }
-  return g_chains;
-}
-
-template <int KS, int NSRC, int NSPLIT, int NOUT, int NCH>
-int launch_tc_impl(const void* src_hi, const void* src_lo, int src_images, const __half* wimg, TcConvParams p,
-              int out_images, cudaStream_t s) {
-  using C = TcCfg<KS, NSRC, NSPLIT, NOUT, NCH>;
-  CUtensorMap tmh, tml;
-  int r = make_act_tmap(&tmh, src_hi, src_images, p.H, p.W, C::BOX_W, C::BOX_H);
-  if (r == 0) r = make_act_tmap(&tml, NSPLIT == 2 ? src_lo : src_hi, src_images, p.H, p.W, C::BOX_W, C::BOX_H);
+// Fills the source-side fields of a phase (tensor maps over fp16 planes [src_images,H,W,64]).
+template <class PC>
+int phase_sources(TcPhase& ph, const void* src_hi, const void* src_lo, int src_images, int H, int W) {
+  int r = make_act_tmap(&ph.tm_hi, src_hi, src_images, H, W, PC::BOX_W, PC::BOX_H);
+  if (r == 0) r = make_act_tmap(&ph.tm_lo, src_lo ? src_lo : src_hi, src_images, H, W, PC::BOX_W, PC::BOX_H);
   if (r != 0) {
-    set_error("cuTensorMapEncodeTiled failed (%d) for images=%d H=%d W=%d", r, src_images, p.H, p.W);
+    set_error("cuTensorMapEncodeTiled failed (%d) for images=%d H=%d W=%d", r, src_images, H, W);
     return PFNL_ERR_CUDA;
   }
-  p.tiles_x = ceil_div(p.W, 8);
-  p.tiles_y = ceil_div(p.H, 16);
-  p.n_tiles = out_images * p.tiles_x * p.tiles_y;
-  if (p.frames < 1) p.frames = 1;
-  p.n_units = p.n_tiles / p.frames;
-  if (p.n_tiles <= 0) return PFNL_OK;
-  int grid = p.n_units < g_num_sms ? p.n_units : g_num_sms;
-  // Cluster size for the weight multicast: the largest of 4/2/1 for which the whole (persistent)
-  // grid is co-resident (1 CTA per SM; 4-CTA clusters fit 132 of the 148 SMs, pairs fit all 148).
+  return PFNL_OK;
+}
+
+// Launches one persistent kernel running phase a and (optionally) phase b on the same units.
+template <class P0, class P1, int NSPLIT>
+int launch_tc(const TcPhase& a, const TcPhase* b, bool phase1_reads_phase0, int H, int W, cudaStream_t s) {
+  using KC = KernelCfg<P0, P1, NSPLIT>;
+  TcCommon cm;
+  memset(&cm, 0, sizeof(cm));
+  cm.H = H;
+  cm.W = W;
+  cm.tiles_x = ceil_div(W, 8);
+  cm.tiles_y = ceil_div(H, 16);
+  cm.nphases = b ? 2 : 1;
+  cm.phase1_reads_phase0 = (b && phase1_reads_phase0) ? 1 : 0;
+  if (a.n_units <= 0) return PFNL_OK;
+  if (b && b->n_units != a.n_units) {
+    set_error("launch_tc: phases must cover the same work units (%d vs %d)", a.n_units, b->n_units);
+    return PFNL_ERR_BAD_ARG;
+  }
+  int grid = a.n_units < g_num_sms ? a.n_units : g_num_sms;
+  // Cluster size for the weight multicast: the largest of 4/2/1 for which the whole persistent grid is
+  // co-resident (1 CTA per SM; 4-CTA clusters fit 132 of the 148 SMs, pairs fit all 148).
   static int max_clusters[5] = {0, 0, -1, 0, -1};  // per kernel instantiation, indexed by cluster size
+  static const int cs_limit = getenv("PFNL_TC_CLUSTER") ? atoi(getenv("PFNL_TC_CLUSTER")) : 1;  // measured on B200: clusters cost more (scheduling, handshake) than the multicast saves
   int cs = 1;
-  static const int cs_limit = getenv("PFNL_TC_CLUSTER") ? atoi(getenv("PFNL_TC_CLUSTER")) : 1;  // measured: no gain on B200 (weights already overlap under PDL), so off by default
   for (int c = 4; c >= 2; c >>= 1) {
     if (c > cs_limit) continue;
     if (max_clusters[c] < 0) {
@@ -649,7 +746,7 @@ int launch_tc_impl(const void* src_hi, const void* src_lo, int src_images, const
       memset(&q, 0, sizeof(q));
       q.gridDim = dim3(g_num_sms / c * c);
       q.blockDim = dim3(kTcThreads);
-      q.dynamicSmemBytes = C::SMEM_BYTES;
+      q.dynamicSmemBytes = KC::SMEM_BYTES;
       cudaLaunchAttribute qa[1];
       qa[0].id = cudaLaunchAttributeClusterDimension;
       qa[0].val.clusterDim.x = c;
@@ -658,14 +755,14 @@ int launch_tc_impl(const void* src_hi, const void* src_lo, int src_images, const
       q.attrs = qa;
       q.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<KS, NSRC, NSPLIT, NOUT, NCH>, &q) != cudaSuccess) {
+      if (cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<P0, P1, NSPLIT>, &q) != cudaSuccess) {
         cudaGetLastError();
         n = 0;
       }
       max_clusters[c] = n;
     }
     const int g = grid / c * c;
-    if (g >= c && g <= max_clusters[c] * c && (g == grid || g * 8 >= grid * 7)) {  // lose < 1/8 of the CTAs at most
+    if (g >= c && g <= max_clusters[c] * c && (g == grid || g * 8 >= grid * 7)) {  // give up < 1/8 of the CTAs
       cs = c;
       grid = g;
       break;
@@ -675,7 +772,7 @@ int launch_tc_impl(const void* src_hi, const void* src_lo, int src_images, const
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kTcThreads);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.dynamicSmemBytes = KC::SMEM_BYTES;
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
   int na = 0;
@@ -698,43 +795,48 @@ int launch_tc_impl(const void* src_hi, const void* src_lo, int src_images, const
   if (tracing) {
     if (!trace_dev) PFNL_CUDA(cudaMalloc((void**)&trace_dev, 3 * 64 * sizeof(long long)));
     PFNL_CUDA(cudaMemsetAsync(trace_dev, 0, 3 * 64 * sizeof(long long), s));
-    p.trace = trace_dev;
+    cm.trace = trace_dev;
   }
-  PFNL_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<KS, NSRC, NSPLIT, NOUT, NCH>, tmh, tml, wimg, p));
+  const TcPhase& bb = b ? *b : a;
+  PFNL_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<P0, P1, NSPLIT>, a, bb, cm));
   if (tracing) {
     long long t[3 * 64];
     PFNL_CUDA(cudaStreamSynchronize(s));
     PFNL_CUDA(cudaMemcpy(t, trace_dev, sizeof(t), cudaMemcpyDeviceToHost));
     const long long t0 = t[0];
-    fprintf(stderr, "[tc-trace] KS=%d NSRC=%d NSPLIT=%d NOUT=%d NCH=%d epi=%d tiles=%d grid=%d (cycles since producer start)\n",
-            KS, NSRC, NSPLIT, NOUT, NCH, p.epi, p.n_tiles, grid);
+    fprintf(stderr,
+            "[tc-trace] phases=%d P0=(KS%d,NSRC%d,N%d,ch%d,epi%d,frames%d) P1=(KS%d,NSRC%d,epi%d,frames%d) NSPLIT=%d "
+            "units=%d grid=%d (cycles since producer start)\n",
+            cm.nphases, P0::KS, P0::NSRC, P0::NOUT, P0::NCH, a.epi, a.frames, P1::KS, P1::NSRC, bb.epi, bb.frames, NSPLIT,
+            a.n_units, grid);
     fprintf(stderr, "  producer issue done :");
-    for (int i = 1; i < 12 && t[i]; ++i) fprintf(stderr, " %lld", t[i] - t0);
+    for (int i = 1; i < 14 && t[i]; ++i) fprintf(stderr, " %lld", t[i] - t0);
     fprintf(stderr, "\n  mma: weights ready %lld ; per tile (data ready, issue done):", t[64] - t0);
-    for (int i = 0; i < 10 && t[64 + 1 + 2 * i]; ++i) fprintf(stderr, " (%lld,%lld)", t[64 + 1 + 2 * i] - t0, t[64 + 2 + 2 * i] - t0);
+    for (int i = 0; i < 12 && t[64 + 1 + 2 * i]; ++i)
+      fprintf(stderr, " (%lld,%lld)", t[64 + 1 + 2 * i] - t0, t[64 + 2 + 2 * i] - t0);
     fprintf(stderr, "\n  epilogue per tile (acc ready, done):");
-    for (int i = 0; i < 10 && t[128 + 2 * i]; ++i) fprintf(stderr, " (%lld,%lld)", t[128 + 2 * i] - t0, t[128 + 1 + 2 * i] - t0);
+    for (int i = 0; i < 12 && t[128 + 2 * i]; ++i)
+      fprintf(stderr, " (%lld,%lld)", t[128 + 2 * i] - t0, t[128 + 1 + 2 * i] - t0);
     fprintf(stderr, "\n");
   }
   return PFNL_OK;
 }
 
-template <int KS, int NSRC, int NSPLIT, int NOUT>
-int launch_tc(const void* src_hi, const void* src_lo, int src_images, const __half* wimg, TcConvParams p,
-              int out_images, cudaStream_t s) {
-  if (KS == 3 && NSPLIT == 2 && x3_chains() == 2)
-    return launch_tc_impl<KS, NSRC, NSPLIT, NOUT, (KS == 3 && NSPLIT == 2) ? 2 : 1>(src_hi, src_lo, src_images, wimg, p,
-                                                                                  out_images, s);
-  return launch_tc_impl<KS, NSRC, NSPLIT, NOUT, 1>(src_hi, src_lo, src_images, wimg, p, out_images, s);
-}
-
-template <int KS, int NSRC, int NSPLIT, int NOUT, int NCH>
+template <class P0, class P1, int NSPLIT>
 int set_attr() {
-  PFNL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KS, NSRC, NSPLIT, NOUT, NCH>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 TcCfg<KS, NSRC, NSPLIT, NOUT, NCH>::SMEM_BYTES));
+  PFNL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<P0, P1, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 KernelCfg<P0, P1, NSPLIT>::SMEM_BYTES));
   return PFNL_OK;
 }
+
+// phase shapes used by the PFRB stack; the split mode uses 2 accumulation chains for 3x3 kernels
+template <int NSPLIT>
+struct Shapes {
+  static constexpr int CH3 = NSPLIT == 2 ? 2 : 1;
+  using C3 = PhaseCfg<3, 1, 64, CH3>;   // conv1, conv2 halves
+  using C10 = PhaseCfg<1, 7, 64, 1>;    // conv10 over the 7 frame slices
+  using CM = PhaseCfg<3, 1, 48, CH3>;   // convmerge1 slice
+};
 
 size_t plane_bytes(int images, int H, int W) { return (size_t)images * H * W * 64 * sizeof(__half); }
 
@@ -788,14 +890,12 @@ int tc_init(TcWeights& tw, int precision, const TcRawWeights& raw, std::vector<v
   tw.nsplit = precision == PFNL_PREC_TC_FP16X3 ? 2 : 1;
   tw.raw = raw;
   int rc;
-  if ((rc = set_attr<3, 1, 1, 64, 1>())) return rc;
-  if ((rc = set_attr<3, 1, 2, 64, 1>())) return rc;
-  if ((rc = set_attr<3, 1, 2, 64, 2>())) return rc;
-  if ((rc = set_attr<1, 7, 1, 64, 1>())) return rc;
-  if ((rc = set_attr<1, 7, 2, 64, 1>())) return rc;
-  if ((rc = set_attr<3, 1, 1, 48, 1>())) return rc;
-  if ((rc = set_attr<3, 1, 2, 48, 1>())) return rc;
-  if ((rc = set_attr<3, 1, 2, 48, 2>())) return rc;
+  if ((rc = set_attr<Shapes<1>::C3, Shapes<1>::C10, 1>())) return rc;
+  if ((rc = set_attr<Shapes<1>::C3, Shapes<1>::C3, 1>())) return rc;
+  if ((rc = set_attr<Shapes<1>::CM, Shapes<1>::CM, 1>())) return rc;
+  if ((rc = set_attr<Shapes<2>::C3, Shapes<2>::C10, 2>())) return rc;
+  if ((rc = set_attr<Shapes<2>::C3, Shapes<2>::C3, 2>())) return rc;
+  if ((rc = set_attr<Shapes<2>::CM, Shapes<2>::CM, 2>())) return rc;
   if ((rc = tc_nl_init())) return rc;
   const int ns = tw.nsplit;
   for (int i = 0; i < PFNL_NUM_BLOCK; ++i) {
@@ -839,69 +939,77 @@ void tc_set_pdl(bool on) { g_pdl = on; }
 
 namespace {
 
-// One PFRB (model/pfnl.py:66-71) on fp16 planes, in place on actA.
+// One PFRB (model/pfnl.py:66-71) on fp16 planes, in place on actA: two persistent launches.
 template <int NSPLIT>
 int pfrb_tc(const TcWeights& tw, TcWorkspace& w, int i, int N, int H, int W, cudaStream_t s, long long* launches,
             Profiler* prof) {
-  TcConvParams p;
-  memset(&p, 0, sizeof(p));
-  p.H = H;
-  p.W = W;
+  using SH = Shapes<NSPLIT>;
+  const int tiles = ceil_div(W, 8) * ceil_div(H, 16);
+  const int units = N * tiles;
   int rc;
-  // inp1[t] = conv1_i(inp0[t])                                   pfnl.py:66
-  p.img_mul = 1;
-  p.img_add = 0;
-  p.frames = kFrames;  // unit = spatial tile x 7 frames
-  p.epi = kEpiActPlanes;
-  p.bias = tw.raw.conv1_b[i];
-  p.out_hi = (__half*)w.actB[0];
-  p.out_lo = (__half*)w.actB[1];
+  TcPhase a, b;
+  // ---- launch A: inp1[t] = conv1_i(inp0[t])  (pfnl.py:66)  ->  base = conv10_i(concat_t inp1[t])  (pfnl.py:67-68)
+  memset(&a, 0, sizeof(a));
+  memset(&b, 0, sizeof(b));
+  if ((rc = phase_sources<typename SH::C3>(a, w.actA[0], w.actA[1], N * kFrames, H, W))) return rc;
+  a.wimg = (const __half*)tw.conv1[i];
+  a.frames = kFrames;
+  a.n_units = units;
+  a.img_mul = 1;
+  a.epi = kEpiActPlanes;
+  a.bias = tw.raw.conv1_b[i];
+  a.out_hi = (__half*)w.actB[0];
+  a.out_lo = (__half*)w.actB[1];
+  // conv10 reads the 7 conv1 outputs of its own unit as 7 K-stages (no concat copy)
+  if ((rc = phase_sources<typename SH::C10>(b, w.actB[0], w.actB[1], N * kFrames, H, W))) return rc;
+  b.wimg = (const __half*)tw.conv10[i];
+  b.frames = 1;
+  b.n_units = units;
+  b.img_mul = kFrames;
+  b.epi = kEpiActPlanes;
+  b.bias = tw.raw.conv10_b[i];
+  b.out_hi = (__half*)w.base[0];
+  b.out_lo = (__half*)w.base[1];
   if (prof) prof->begin(kProfConv1, s);
-  rc = launch_tc<3, 1, NSPLIT, 64>(w.actA[0], w.actA[1], N * kFrames, (const __half*)tw.conv1[i], p, N * kFrames, s);
+  rc = launch_tc<typename SH::C3, typename SH::C10, NSPLIT>(a, &b, true, H, W, s);
   if (prof) prof->end(s);
   if (rc) return rc;
-  // base = conv10_i(concat_t inp1[t])                            pfnl.py:67-68  (7 K-slices, no concat copy)
-  p.img_mul = kFrames;
-  p.frames = 1;
-  p.bias = tw.raw.conv10_b[i];
-  p.out_hi = (__half*)w.base[0];
-  p.out_lo = (__half*)w.base[1];
-  if (prof) prof->begin(kProfConv10, s);
-  rc = launch_tc<1, 7, NSPLIT, 64>(w.actB[0], w.actB[1], N * kFrames, (const __half*)tw.conv10[i], p, N, s);
-  if (prof) prof->end(s);
-  if (rc) return rc;
-  // conv2_i(concat[base, inp1[t]]) = conv(base; W2[:,:,0:64]) + conv(inp1[t]; W2[:,:,64:128]):
-  // the base half is identical for the 7 frames -> computed once (fp32 partial sums)
-  p.img_mul = 1;
-  p.epi = kEpiPartialF32;
-  p.accumulate = 0;
-  p.bias = nullptr;
-  p.out_f32 = w.pbase;
-  if (prof) prof->begin(kProfOther, s);
-  rc = launch_tc<3, 1, NSPLIT, 64>(w.base[0], w.base[1], N, (const __half*)tw.conv2b[i], p, N, s);
-  if (prof) prof->end(s);
-  if (rc) return rc;
-  // inp0[t] += leaky_relu(partial + conv(inp1[t]) + bias)         pfnl.py:70-71
-  p.epi = kEpiResPlanes;
-  p.frames = kFrames;
-  p.bias = tw.raw.conv2_b[i];
-  p.pbase = w.pbase;
-  p.pb_div = kFrames;
-  p.res_hi = (const __half*)w.actA[0];
-  p.res_lo = (const __half*)w.actA[1];
-  p.out_hi = (__half*)w.actA[0];
-  p.out_lo = (__half*)w.actA[1];
+  // ---- launch B: conv2_i(concat[base, inp1[t]]) = conv(base; W2[:,:,0:64]) + conv(inp1[t]; W2[:,:,64:128]):
+  //      the base half is identical for the 7 frames -> computed once per unit (fp32 partial sums), then
+  //      inp0[t] += leaky_relu(partial + conv(inp1[t]) + bias)                          (pfnl.py:69-71)
+  memset(&a, 0, sizeof(a));
+  memset(&b, 0, sizeof(b));
+  if ((rc = phase_sources<typename SH::C3>(a, w.base[0], w.base[1], N, H, W))) return rc;
+  a.wimg = (const __half*)tw.conv2b[i];
+  a.frames = 1;
+  a.n_units = units;
+  a.img_mul = 1;
+  a.epi = kEpiPartialF32;
+  a.out_f32 = w.pbase;
+  if ((rc = phase_sources<typename SH::C3>(b, w.actB[0], w.actB[1], N * kFrames, H, W))) return rc;
+  b.wimg = (const __half*)tw.conv2f[i];
+  b.frames = kFrames;
+  b.n_units = units;
+  b.img_mul = 1;
+  b.epi = kEpiResPlanes;
+  b.bias = tw.raw.conv2_b[i];
+  b.pbase = w.pbase;
+  b.res_hi = (const __half*)w.actA[0];
+  b.res_lo = (const __half*)w.actA[1];
+  b.out_hi = (__half*)w.actA[0];
+  b.out_lo = (__half*)w.actA[1];
   if (prof) prof->begin(kProfConv2, s);
-  rc = launch_tc<3, 1, NSPLIT, 64>(w.actB[0], w.actB[1], N * kFrames, (const __half*)tw.conv2f[i], p, N * kFrames, s);
+  rc = launch_tc<typename SH::C3, typename SH::C3, NSPLIT>(a, &b, false, H, W, s);
   if (prof) prof->end(s);
   if (rc) return rc;
-  *launches += 4;
+  *launches += 2;
   return PFNL_OK;
 }
 
 template <int NSPLIT>
 int trunk_tc(const TcWeights& tw, TcWorkspace& w, const float* inp21, int N, int H, int W, float* merge,
              cudaStream_t s, long long* launches, Profiler* prof) {
+  using SH = Shapes<NSPLIT>;
   int rc;
   dim3 grid(ceil_div(W, 16) * ceil_div(H, 16), N * kFrames);
   if (prof) prof->begin(kProfConv0, s);
@@ -913,21 +1021,23 @@ int trunk_tc(const TcWeights& tw, TcWorkspace& w, const float* inp21, int N, int
   for (int i = 0; i < PFNL_NUM_BLOCK; ++i)
     if ((rc = pfrb_tc<NSPLIT>(tw, w, i, N, H, W, s, launches, prof))) return rc;
   // merge = convmerge1(concat_t inp0[t])                          pfnl.py:73-74: 7 accumulating launches
-  TcConvParams p;
-  memset(&p, 0, sizeof(p));
-  p.H = H;
-  p.W = W;
-  p.img_mul = kFrames;
-  p.out_f32 = merge;
+  const int units = N * ceil_div(W, 8) * ceil_div(H, 16);
   const size_t per = (size_t)NSPLIT * 9 * 48 * 128;
   if (prof) prof->begin(kProfMerge1, s);
   for (int t = 0; t < kFrames; ++t) {
-    p.img_add = t;
-    p.epi = t == kFrames - 1 ? kEpiFinalF32 : kEpiPartialF32;
-    p.accumulate = t > 0;
-    p.bias = t == kFrames - 1 ? tw.raw.merge1_b : nullptr;
-    rc = launch_tc<3, 1, NSPLIT, 48>(w.actA[0], w.actA[1], N * kFrames,
-                                     (const __half*)((const uint8_t*)tw.merge1 + per * t), p, N, s);
+    TcPhase a;
+    memset(&a, 0, sizeof(a));
+    if ((rc = phase_sources<typename SH::CM>(a, w.actA[0], w.actA[1], N * kFrames, H, W))) return rc;
+    a.wimg = (const __half*)((const uint8_t*)tw.merge1 + per * t);
+    a.frames = 1;
+    a.n_units = units;
+    a.img_mul = kFrames;
+    a.img_add = t;
+    a.epi = t == kFrames - 1 ? kEpiFinalF32 : kEpiPartialF32;
+    a.accumulate = t > 0;
+    a.bias = t == kFrames - 1 ? tw.raw.merge1_b : nullptr;
+    a.out_f32 = merge;
+    rc = launch_tc<typename SH::CM, typename SH::CM, NSPLIT>(a, nullptr, false, H, W, s);
     if (rc) return rc;
   }
   if (prof) prof->end(s);

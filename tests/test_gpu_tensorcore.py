@@ -145,6 +145,18 @@ def test_forward_batch16_tc_matches_per_clip(tc_engines):
     assert np.abs(yb[:2] - ref).max() <= 1e-3
 
 
+@pytest.mark.parametrize("prec,tol", [("fp16x3", 1e-3), ("fp16", 5e-3)])
+def test_forward_more_units_than_sms(tc_engines, prec, tol):
+    """2 clips x 7 x 128x96: 192 work units > 148 SMs, so persistent CTAs own several units per phase
+    (conv1 -> conv10 and partial-sum -> conv2 run phase-ordered on the CTA's own units)."""
+    x = R.make_input(2, 128, 96, seed=11)
+    y = tc_engines[(prec, "B")].forward(cu(x)).cpu().numpy()
+    ref = R.pfnl_forward(x, R.make_weights("B"), backend="torch")
+    err = np.abs(y - ref).max()
+    print(f"{prec} 2x128x96: max-abs {err:.3e}")
+    assert err <= tol
+
+
 def test_forward_128_fp16x3(tc_engines):
     x = R.make_input(1, 128, 128, seed=5)
     y = tc_engines[("fp16x3", "B")].forward(cu(x)).cpu().numpy()
