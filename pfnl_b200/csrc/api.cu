@@ -77,6 +77,9 @@ struct pfnl_handle {
   int precision = 0;
   // raw HWIO weights on the device (fp32)
   float *nl_g_w = nullptr, *nl_g_b = nullptr, *nl_w_w = nullptr, *nl_w_b = nullptr;
+  // g and w folded: w(softmax(S)*(X*Wg+bg)) = softmax(S)*X*(Wg*Ww) + (bg*Ww+bw) because softmax rows sum
+  // to 1 and nothing non-linear sits between the two 1x1 convs (utils.py:26,64,67)
+  float *nl_gw_w = nullptr, *nl_gw_b = nullptr;
   float *conv0_w = nullptr, *conv0_b = nullptr;
   float* conv1_w[PFNL_NUM_BLOCK] = {};
   float* conv1_b[PFNL_NUM_BLOCK] = {};
@@ -258,12 +261,12 @@ int forward_launches(pfnl_handle* h, const float* lr, int N, int H, int W, float
   } else {
     h->prof.begin(kProfNonlocal, s);
     // NonLocalBlock                                         pfnl.py:58, utils.py:18-71
-    if ((rc = launch_nl_linear(w.tokens, N * L, h->nl_g_w, h->nl_g_b, w.g, s))) return rc;
-    if ((rc = launch_nl_flash_ffma(w.tokens, w.g, N, L, w.yatt, s))) return rc;
+    // Q = K = V = X (theta = phi = input, utils.py:33-34,41-42; g folded into the output linear)
+    if ((rc = launch_nl_flash_ffma(w.tokens, w.tokens, N, L, w.yatt, s))) return rc;
     // inp0 += depth_to_space(w(y))                          pfnl.py:59-60
-    if ((rc = launch_nl_linear_scatter(w.yatt, lr, N, H, W, h->nl_w_w, h->nl_w_b, w.inp21, s))) return rc;
+    if ((rc = launch_nl_linear_scatter(w.yatt, lr, N, H, W, h->nl_gw_w, h->nl_gw_b, w.inp21, s))) return rc;
     h->prof.end(s);
-    h->launches += 3;
+    h->launches += 2;
   }
   if (h->precision == PFNL_PREC_FP32) {
     // conv0 on each frame                                   pfnl.py:61-62
@@ -352,6 +355,28 @@ int pfnl_create(pfnl_handle** out, int device, const pfnl_weights* wts, int prec
   TRY(upload(h, wts->nl_g_bias, kNL, &h->nl_g_b));
   TRY(upload(h, wts->nl_w_kernel, kNL * kNL, &h->nl_w_w));
   TRY(upload(h, wts->nl_w_bias, kNL, &h->nl_w_b));
+  {
+    // folded non-local output linear, computed in double on the host
+    if (!wts->nl_g_kernel || !wts->nl_g_bias || !wts->nl_w_kernel || !wts->nl_w_bias) {
+      set_error("pfnl_create: a weight pointer is NULL");
+      rc = PFNL_ERR_BAD_ARG;
+      goto fail;
+    }
+    std::vector<float> gw(kNL * kNL), gb(kNL);
+    for (int i = 0; i < kNL; ++i)
+      for (int j = 0; j < kNL; ++j) {
+        double a = 0.0;
+        for (int k = 0; k < kNL; ++k) a += (double)wts->nl_g_kernel[i * kNL + k] * (double)wts->nl_w_kernel[k * kNL + j];
+        gw[i * kNL + j] = (float)a;
+      }
+    for (int j = 0; j < kNL; ++j) {
+      double a = (double)wts->nl_w_bias[j];
+      for (int k = 0; k < kNL; ++k) a += (double)wts->nl_g_bias[k] * (double)wts->nl_w_kernel[k * kNL + j];
+      gb[j] = (float)a;
+    }
+    TRY(upload(h, gw.data(), kNL * kNL, &h->nl_gw_w));
+    TRY(upload(h, gb.data(), kNL, &h->nl_gw_b));
+  }
   TRY(upload(h, wts->conv0_kernel, 75 * 64, &h->conv0_w));
   TRY(upload(h, wts->conv0_bias, 64, &h->conv0_b));
   for (int i = 0; i < PFNL_NUM_BLOCK; ++i) {
@@ -655,10 +680,9 @@ int pfnl_nonlocal(pfnl_handle* h, const float* tokens, int N, int L, float* out,
   int rc = ensure_workspace(h, N, 2, 2 * L);
   if (rc) return rc;
   Workspace w = carve(h->ws, h->precision, N, 2, 2 * L);
-  if ((rc = launch_nl_linear(tokens, N * L, h->nl_g_w, h->nl_g_b, w.g, s))) return rc;
-  if ((rc = launch_nl_flash_ffma(tokens, w.g, N, L, w.yatt, s))) return rc;
-  if ((rc = launch_nl_linear(w.yatt, N * L, h->nl_w_w, h->nl_w_b, out, s))) return rc;
-  h->launches += 3;
+  if ((rc = launch_nl_flash_ffma(tokens, tokens, N, L, w.yatt, s))) return rc;
+  if ((rc = launch_nl_linear(w.yatt, N * L, h->nl_gw_w, h->nl_gw_b, out, s))) return rc;
+  h->launches += 2;
   return PFNL_OK;
 }
 

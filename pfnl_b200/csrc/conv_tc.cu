@@ -69,6 +69,11 @@ struct TcPhase {
   float* out_f32;            // [out_images][H][W][NOUT]
 };
 
+constexpr int kTcMaxPhases = 7;
+struct TcProgram {
+  TcPhase ph[kTcMaxPhases];
+};
+
 struct TcCommon {
   int H, W, tiles_x, tiles_y;
   int nphases;
@@ -102,7 +107,7 @@ struct KernelCfg {
   static constexpr int W_BYTES = cmax(W0, W1);
   static constexpr int SLOT_BYTES = (cmax(P0::PATCH_BYTES, P1::PATCH_BYTES) + 1023) / 1024 * 1024;
   static constexpr int SMEM_MAX = 227 * 1024;
-  static constexpr int CTRL_BYTES = 1024;
+  static constexpr int CTRL_BYTES = 3072;
   static constexpr int TOTAL_SLOTS = (SMEM_MAX - 1024 - CTRL_BYTES - W_BYTES) / SLOT_BYTES;
   // ONE ring of patch slots shared by the hi and lo planes (loads alternate hi, lo, hi, lo ...)
   static constexpr int NS = TOTAL_SLOTS > 6 ? 6 : TOTAL_SLOTS;
@@ -129,7 +134,7 @@ struct TcCtrl {
   uint64_t full[8], empty[8];
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
-  float bias[2][64];
+  float bias[kTcMaxPhases][64];
 };
 
 struct TcRing {  // ring slot cursor (producer and MMA issuer keep identical copies)
@@ -454,9 +459,11 @@ __device__ __forceinline__ void epilogue_phase(const TcPhase& P, const TcCommon&
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Phase 0 has shape P0, phases 1..nphases-1 have shape P1 (conv1 -> conv10; partial sums -> conv2;
+// the 7 accumulating frame slices of convmerge1).
 template <class P0, class P1, int NSPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1)
-    conv_tc_kernel(const __grid_constant__ TcPhase ph0, const __grid_constant__ TcPhase ph1, const TcCommon cm) {
+    conv_tc_kernel(const __grid_constant__ TcProgram prog, const TcCommon cm) {
   using KC = KernelCfg<P0, P1, NSPLIT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -464,6 +471,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   uint8_t* ring = wsm + KC::W_BYTES;   // [NS][SLOT_BYTES]
   TcCtrl* ctl = reinterpret_cast<TcCtrl*>(ring + KC::NS * KC::SLOT_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const TcPhase& ph0 = prog.ph[0];
 
   // ---- prologue: touches only weights / biases (never written by any kernel); overlaps the previous
   //      kernel's tail under programmatic dependent launch
@@ -485,15 +493,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     tma_prefetch_desc(&ph0.tm_hi);
     if (NSPLIT == 2) tma_prefetch_desc(&ph0.tm_lo);
     mbar_arrive_expect_tx(&ctl->wfull, KC::W0);  // this CTA receives the whole image
-    if (cm.nphases > 1) {  // warm L2 with the second phase's weight image (first touch is a DRAM read)
+    if (cm.nphases > 1) {  // warm L2 with the next phase's weight image (first touch is a DRAM read)
       const int off = blockIdx.x * 16384;
       if (off < KC::W1)
-        l2_prefetch_bulk(reinterpret_cast<const uint8_t*>(ph1.wimg) + off, (KC::W1 - off) < 16384 ? (KC::W1 - off) : 16384);
+        l2_prefetch_bulk(reinterpret_cast<const uint8_t*>(prog.ph[1].wimg) + off,
+                         (KC::W1 - off) < 16384 ? (KC::W1 - off) : 16384);
     }
   }
-  if (tid < 64) {
-    ctl->bias[0][tid] = (ph0.bias != nullptr && tid < P0::NOUT) ? ph0.bias[tid] : 0.f;
-    ctl->bias[1][tid] = (cm.nphases > 1 && ph1.bias != nullptr && tid < P1::NOUT) ? ph1.bias[tid] : 0.f;
+  for (int i = tid; i < kTcMaxPhases * 64; i += kTcThreads) {
+    const int pi = i >> 6, c = i & 63;
+    const float* bp = pi < cm.nphases ? prog.ph[pi].bias : nullptr;
+    const int nout = pi == 0 ? P0::NOUT : P1::NOUT;
+    ctl->bias[pi][c] = (bp != nullptr && c < nout) ? bp[c] : 0.f;
   }
   if (warp == 1) {
     tmem_alloc(&ctl->tmem_base, KC::TMEM_COLS);
@@ -518,27 +529,33 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       int tcount = 0;
       TC_TRACE(0, 0);
       producer_phase<P0, KC, NSPLIT>(ph0, cm, ring, ctl, rg, tcount);
-      if (cm.nphases > 1) {
-        // swap the weight image once every MMA of phase 0 has completed, and make sure the phase-0
-        // outputs (written with generic-proxy stores by this CTA) are visible to the TMA (async proxy)
-        tma_prefetch_desc(&ph1.tm_hi);
-        if (NSPLIT == 2) tma_prefetch_desc(&ph1.tm_lo);
-        mbar_wait(&ctl->wfree, 0);
+      for (int pi = 1; pi < cm.nphases; ++pi) {
+        const TcPhase& ph = prog.ph[pi];
+        // swap the weight image once every MMA of the previous phase has completed
+        tma_prefetch_desc(&ph.tm_hi);
+        if (NSPLIT == 2) tma_prefetch_desc(&ph.tm_lo);
+        if (pi + 1 < cm.nphases) {
+          const int off = blockIdx.x * 16384;
+          if (off < KC::W1)
+            l2_prefetch_bulk(reinterpret_cast<const uint8_t*>(prog.ph[pi + 1].wimg) + off,
+                             (KC::W1 - off) < 16384 ? (KC::W1 - off) : 16384);
+        }
+        mbar_wait(&ctl->wfree, (pi - 1) & 1);
         mbar_arrive_expect_tx(&ctl->wfull, KC::W1);
         if (cs > 1) {
-          // peers may only overwrite my weights once I am done with phase 0 (and vice versa): tell every
-          // CTA of the cluster that I am ready, then wait until all of them are
+          // peers may only overwrite my weights once I am done with the previous phase (and vice versa):
+          // tell every CTA of the cluster that I am ready, then wait until all of them are
           for (uint32_t r = 0; r < cs; ++r) mbar_arrive_remote(&ctl->peers_ready, r);
-          mbar_wait_cluster(&ctl->peers_ready, 0);
+          mbar_wait_cluster(&ctl->peers_ready, (pi - 1) & 1);
         }
-        load_weights_slice<KC::W1>(wsm, ph1.wimg, &ctl->wfull, cs, cr);  // needs only the MMAs to have drained
+        load_weights_slice<KC::W1>(wsm, ph.wimg, &ctl->wfull, cs, cr);  // needs only the MMAs to have drained
         if (cm.phase1_reads_phase0) {
-          // phase-1 patches are this CTA's own phase-0 outputs (conv10 <- conv1): the generic-proxy
-          // stores must be visible to the TMA (async proxy) first
-          mbar_wait(&ctl->stores_done, 0);
+          // this phase's patches are the CTA's own outputs of the previous phase (conv10 <- conv1): the
+          // generic-proxy stores must be visible to the TMA (async proxy) first
+          mbar_wait(&ctl->stores_done, (pi - 1) & 1);
           fence_proxy_async_all();
         }
-        producer_phase<P1, KC, NSPLIT>(ph1, cm, ring, ctl, rg, tcount);
+        producer_phase<P1, KC, NSPLIT>(ph, cm, ring, ctl, rg, tcount);
       }
     }
   } else if (warp == 1) {
@@ -549,26 +566,26 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     fence_after_sync();
     if (lane == 0) TC_TRACE(1, 0);
     mma_phase<P0, KC, NSPLIT>(ph0, cm, wsm, ring, ctl, tmem, rg, it, lane);
-    if (cm.nphases > 1) {
+    for (int pi = 1; pi < cm.nphases; ++pi) {
       if (elect_one()) mma_commit(&ctl->wfree);  // arrives when every MMA issued so far has completed
       __syncwarp();
-      mbar_wait(&ctl->wfull, 1);
+      mbar_wait(&ctl->wfull, pi & 1);
       fence_after_sync();
-      mma_phase<P1, KC, NSPLIT>(ph1, cm, wsm, ring, ctl, tmem, rg, it, lane);
+      mma_phase<P1, KC, NSPLIT>(prog.ph[pi], cm, wsm, ring, ctl, tmem, rg, it, lane);
     }
   } else {
     // ===================== epilogue (warps 2..17) =====================
     int it = 0;
     epilogue_phase<P0, KC, NSPLIT>(ph0, cm, ctl, ctl->bias[0], tmem, it, warp, lane);
-    if (cm.nphases > 1) {
+    for (int pi = 1; pi < cm.nphases; ++pi) {
       if (cm.phase1_reads_phase0) {
-        // phase-0 stores of this thread -> visible device-wide and to the async proxy before phase 1 reads them
+        // this thread's stores -> visible device-wide and to the async proxy before the next phase reads them
         __threadfence();
         fence_proxy_async_all();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl->stores_done);
       }
-      epilogue_phase<P1, KC, NSPLIT>(ph1, cm, ctl, ctl->bias[1], tmem, it, warp, lane);
+      epilogue_phase<P1, KC, NSPLIT>(prog.ph[pi], cm, ctl, ctl->bias[pi], tmem, it, warp, lane);
     }
   }
   fence_before_sync();
@@ -626,69 +643,96 @@ __global__ void planes_to_f32_kernel(const __half* __restrict__ hi, const __half
 }
 
 // conv0 (5x5, 3->64, leaky_relu; model/pfnl.py:48,61-62) writing fp16 planes.  K = 75 is too
-// small/odd for the MMA path (0.2 % of the FLOPs): CUDA cores, same structure as conv0_kernel.
+// small/odd for the MMA path (0.2 % of the FLOPs): CUDA cores.  Tile = 16x16 pixels of one frame;
+// thread = 4 consecutive pixels x 16 output channels (one smem read per 8 FMAs; the four lanes that
+// share a pixel quad write one contiguous 128-byte pixel row of the output plane).
 template <int NSPLIT>
 __global__ void __launch_bounds__(256, 2) conv0_planes_kernel(const float* __restrict__ inp21, int H, int W,
                                                            const float* __restrict__ w, const float* __restrict__ bias,
                                                            __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
   __shared__ __align__(16) float wsm[75 * 64];
-  __shared__ float patch[20 * 20 * 3];
+  constexpr int PP = 61;  // patch row pitch (floats): keeps the 8 pixel quads of a warp on 8 different banks
+  __shared__ float patch[20 * PP];
   const int tid = threadIdx.x;
   const int tiles_x = ceil_div(W, 16);
   const int ty = blockIdx.x / tiles_x, tx = blockIdx.x % tiles_x;
   const int img = blockIdx.y;
   const int n = img / kFrames, t = img % kFrames;
   const int y0 = ty * 16, x0 = tx * 16;
-  for (int i = tid; i < 75 * 64; i += 256) wsm[i] = w[i];
+  // weights permuted to [k][j4][g][4]: the 4 channel groups of a warp read 4 consecutive 16-byte chunks
+  for (int i = tid; i < 75 * 64; i += 256) {
+    const int kk = i >> 6, co = i & 63;
+    wsm[kk * 64 + ((co >> 2) & 3) * 16 + (co >> 4) * 4 + (co & 3)] = w[i];
+  }
   for (int i = tid; i < 20 * 20 * 3; i += 256) {
     int c = i % 3, pp = i / 3;
     int py = pp / 20, px = pp % 20;
     int gy = y0 + py - 2, gx = x0 + px - 2;
     float v = 0.f;
     if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = inp21[(((long long)n * H + gy) * W + gx) * 21 + t * 3 + c];
-    patch[i] = v;
+    patch[py * PP + px * 3 + c] = v;
   }
   __syncthreads();
-  const int py = tid >> 4, px = tid & 15;
-  float acc[64];
+  const int g = tid & 3;        // output channels g*16 .. g*16+15
+  const int quad = tid >> 2;    // 64 pixel quads: row = quad / 4, columns (quad % 4)*4 .. +3
+  const int py = quad >> 2, px0 = (quad & 3) * 4;
+  float acc[4][16];
 #pragma unroll
-  for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
 #pragma unroll 1
   for (int dy = 0; dy < 5; ++dy) {
-#pragma unroll
+#pragma unroll 1
     for (int dx = 0; dx < 5; ++dx) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float av = patch[((py + dy) * 20 + px + dx) * 3 + c];
-        const float4* wr = reinterpret_cast<const float4*>(wsm + ((dy * 5 + dx) * 3 + c) * 64);
+        const float* pr = patch + (py + dy) * PP + (px0 + dx) * 3 + c;
+        const float a0 = pr[0], a1 = pr[3], a2 = pr[6], a3 = pr[9];
+        const float4* wr = reinterpret_cast<const float4*>(wsm + ((dy * 5 + dx) * 3 + c) * 64 + g * 4);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 b = wr[j];
-          acc[4 * j + 0] = fmaf(av, b.x, acc[4 * j + 0]);
-          acc[4 * j + 1] = fmaf(av, b.y, acc[4 * j + 1]);
-          acc[4 * j + 2] = fmaf(av, b.z, acc[4 * j + 2]);
-          acc[4 * j + 3] = fmaf(av, b.w, acc[4 * j + 3]);
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b = wr[j4 * 4];
+          acc[0][4 * j4 + 0] = fmaf(a0, b.x, acc[0][4 * j4 + 0]);
+          acc[0][4 * j4 + 1] = fmaf(a0, b.y, acc[0][4 * j4 + 1]);
+          acc[0][4 * j4 + 2] = fmaf(a0, b.z, acc[0][4 * j4 + 2]);
+          acc[0][4 * j4 + 3] = fmaf(a0, b.w, acc[0][4 * j4 + 3]);
+          acc[1][4 * j4 + 0] = fmaf(a1, b.x, acc[1][4 * j4 + 0]);
+          acc[1][4 * j4 + 1] = fmaf(a1, b.y, acc[1][4 * j4 + 1]);
+          acc[1][4 * j4 + 2] = fmaf(a1, b.z, acc[1][4 * j4 + 2]);
+          acc[1][4 * j4 + 3] = fmaf(a1, b.w, acc[1][4 * j4 + 3]);
+          acc[2][4 * j4 + 0] = fmaf(a2, b.x, acc[2][4 * j4 + 0]);
+          acc[2][4 * j4 + 1] = fmaf(a2, b.y, acc[2][4 * j4 + 1]);
+          acc[2][4 * j4 + 2] = fmaf(a2, b.z, acc[2][4 * j4 + 2]);
+          acc[2][4 * j4 + 3] = fmaf(a2, b.w, acc[2][4 * j4 + 3]);
+          acc[3][4 * j4 + 0] = fmaf(a3, b.x, acc[3][4 * j4 + 0]);
+          acc[3][4 * j4 + 1] = fmaf(a3, b.y, acc[3][4 * j4 + 1]);
+          acc[3][4 * j4 + 2] = fmaf(a3, b.z, acc[3][4 * j4 + 2]);
+          acc[3][4 * j4 + 3] = fmaf(a3, b.w, acc[3][4 * j4 + 3]);
         }
       }
     }
   }
-  const int gy = y0 + py, gx = x0 + px;
-  if (gy < H && gx < W) {
-    const long long pix = ((long long)img * H + gy) * W + gx;
+  const int gy = y0 + py;
+  if (gy < H) {
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 8) {
-      __align__(16) __half oh[8];
-      __align__(16) __half ol[8];
+    for (int i = 0; i < 4; ++i) {
+      const int gx = x0 + px0 + i;
+      if (gx >= W) continue;
+      const long long pix = ((long long)img * H + gy) * W + gx;
+      U256 oh, ol;
+      __half* ph = reinterpret_cast<__half*>(&oh);
+      __half* pl = reinterpret_cast<__half*>(&ol);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float v = lrelu(acc[c0 + j] + bias[c0 + j]);
+      for (int j = 0; j < 16; ++j) {
+        const float v = lrelu(acc[i][j] + bias[g * 16 + j]);
         if (NSPLIT == 2)
-          split_half(v, oh[j], ol[j]);
+          split_half(v, ph[j], pl[j]);
         else
-          oh[j] = __float2half_rn(v);
+          ph[j] = __float2half_rn(v);
       }
-      *reinterpret_cast<uint4*>(out_hi + pix * 64 + c0) = *reinterpret_cast<const uint4*>(oh);
-      if (NSPLIT == 2) *reinterpret_cast<uint4*>(out_lo + pix * 64 + c0) = *reinterpret_cast<const uint4*>(ol);
+      st256(out_hi + pix * 64 + g * 16, oh);
+      if (NSPLIT == 2) st256(out_lo + pix * 64 + g * 16, ol);
     }
   }
 }
@@ -718,7 +762,8 @@ int phase_sources(TcPhase& ph, const void* src_hi, const void* src_lo, int src_i
 
 // Launches one persistent kernel running phase a and (optionally) phase b on the same units.
 template <class P0, class P1, int NSPLIT>
-int launch_tc(const TcPhase& a, const TcPhase* b, bool phase1_reads_phase0, int H, int W, cudaStream_t s) {
+int launch_tc(const TcProgram& prog, int nphases, bool phase1_reads_phase0, int H, int W, cudaStream_t s) {
+  const TcPhase& a = prog.ph[0];
   using KC = KernelCfg<P0, P1, NSPLIT>;
   TcCommon cm;
   memset(&cm, 0, sizeof(cm));
@@ -726,13 +771,14 @@ int launch_tc(const TcPhase& a, const TcPhase* b, bool phase1_reads_phase0, int 
   cm.W = W;
   cm.tiles_x = ceil_div(W, 8);
   cm.tiles_y = ceil_div(H, 16);
-  cm.nphases = b ? 2 : 1;
-  cm.phase1_reads_phase0 = (b && phase1_reads_phase0) ? 1 : 0;
+  cm.nphases = nphases;
+  cm.phase1_reads_phase0 = (nphases > 1 && phase1_reads_phase0) ? 1 : 0;
   if (a.n_units <= 0) return PFNL_OK;
-  if (b && b->n_units != a.n_units) {
-    set_error("launch_tc: phases must cover the same work units (%d vs %d)", a.n_units, b->n_units);
-    return PFNL_ERR_BAD_ARG;
-  }
+  for (int i = 1; i < nphases; ++i)
+    if (prog.ph[i].n_units != a.n_units) {
+      set_error("launch_tc: phases must cover the same work units (%d vs %d)", a.n_units, prog.ph[i].n_units);
+      return PFNL_ERR_BAD_ARG;
+    }
   int grid = a.n_units < g_num_sms ? a.n_units : g_num_sms;
   // Cluster size for the weight multicast: the largest of 4/2/1 for which the whole persistent grid is
   // co-resident (1 CTA per SM; 4-CTA clusters fit 132 of the 148 SMs, pairs fit all 148).
@@ -797,8 +843,8 @@ int launch_tc(const TcPhase& a, const TcPhase* b, bool phase1_reads_phase0, int 
     PFNL_CUDA(cudaMemsetAsync(trace_dev, 0, 3 * 64 * sizeof(long long), s));
     cm.trace = trace_dev;
   }
-  const TcPhase& bb = b ? *b : a;
-  PFNL_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<P0, P1, NSPLIT>, a, bb, cm));
+  const TcPhase& bb = prog.ph[nphases > 1 ? 1 : 0];
+  PFNL_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<P0, P1, NSPLIT>, prog, cm));
   if (tracing) {
     long long t[3 * 64];
     PFNL_CUDA(cudaStreamSynchronize(s));
@@ -947,7 +993,9 @@ int pfrb_tc(const TcWeights& tw, TcWorkspace& w, int i, int N, int H, int W, cud
   const int tiles = ceil_div(W, 8) * ceil_div(H, 16);
   const int units = N * tiles;
   int rc;
-  TcPhase a, b;
+  TcProgram prog;
+  TcPhase& a = prog.ph[0];
+  TcPhase& b = prog.ph[1];
   // ---- launch A: inp1[t] = conv1_i(inp0[t])  (pfnl.py:66)  ->  base = conv10_i(concat_t inp1[t])  (pfnl.py:67-68)
   memset(&a, 0, sizeof(a));
   memset(&b, 0, sizeof(b));
@@ -971,7 +1019,7 @@ int pfrb_tc(const TcWeights& tw, TcWorkspace& w, int i, int N, int H, int W, cud
   b.out_hi = (__half*)w.base[0];
   b.out_lo = (__half*)w.base[1];
   if (prof) prof->begin(kProfConv1, s);
-  rc = launch_tc<typename SH::C3, typename SH::C10, NSPLIT>(a, &b, true, H, W, s);
+  rc = launch_tc<typename SH::C3, typename SH::C10, NSPLIT>(prog, 2, true, H, W, s);
   if (prof) prof->end(s);
   if (rc) return rc;
   // ---- launch B: conv2_i(concat[base, inp1[t]]) = conv(base; W2[:,:,0:64]) + conv(inp1[t]; W2[:,:,64:128]):
@@ -999,7 +1047,7 @@ int pfrb_tc(const TcWeights& tw, TcWorkspace& w, int i, int N, int H, int W, cud
   b.out_hi = (__half*)w.actA[0];
   b.out_lo = (__half*)w.actA[1];
   if (prof) prof->begin(kProfConv2, s);
-  rc = launch_tc<typename SH::C3, typename SH::C3, NSPLIT>(a, &b, false, H, W, s);
+  rc = launch_tc<typename SH::C3, typename SH::C3, NSPLIT>(prog, 2, false, H, W, s);
   if (prof) prof->end(s);
   if (rc) return rc;
   *launches += 2;
@@ -1020,12 +1068,13 @@ int trunk_tc(const TcWeights& tw, TcWorkspace& w, const float* inp21, int N, int
   *launches += 1;
   for (int i = 0; i < PFNL_NUM_BLOCK; ++i)
     if ((rc = pfrb_tc<NSPLIT>(tw, w, i, N, H, W, s, launches, prof))) return rc;
-  // merge = convmerge1(concat_t inp0[t])                          pfnl.py:73-74: 7 accumulating launches
+  // merge = convmerge1(concat_t inp0[t])                          pfnl.py:73-74: ONE launch, 7 phases - frame slice t
+  // of the K = 7*576 contraction per phase, fp32 partial sums accumulated in place by the same threads
   const int units = N * ceil_div(W, 8) * ceil_div(H, 16);
   const size_t per = (size_t)NSPLIT * 9 * 48 * 128;
-  if (prof) prof->begin(kProfMerge1, s);
+  TcProgram prog;
   for (int t = 0; t < kFrames; ++t) {
-    TcPhase a;
+    TcPhase& a = prog.ph[t];
     memset(&a, 0, sizeof(a));
     if ((rc = phase_sources<typename SH::CM>(a, w.actA[0], w.actA[1], N * kFrames, H, W))) return rc;
     a.wimg = (const __half*)((const uint8_t*)tw.merge1 + per * t);
@@ -1037,11 +1086,12 @@ int trunk_tc(const TcWeights& tw, TcWorkspace& w, const float* inp21, int N, int
     a.accumulate = t > 0;
     a.bias = t == kFrames - 1 ? tw.raw.merge1_b : nullptr;
     a.out_f32 = merge;
-    rc = launch_tc<typename SH::CM, typename SH::CM, NSPLIT>(a, nullptr, false, H, W, s);
-    if (rc) return rc;
   }
+  if (prof) prof->begin(kProfMerge1, s);
+  rc = launch_tc<typename SH::CM, typename SH::CM, NSPLIT>(prog, kFrames, false, H, W, s);
   if (prof) prof->end(s);
-  *launches += kFrames;
+  if (rc) return rc;
+  *launches += 1;
   return PFNL_OK;
 }
 

@@ -15,9 +15,10 @@
 
 namespace pfnl {
 
-// Y[rows,84] = X[rows,84] * Wm[84,84] + b.  CTA = 48 rows, 252 active threads:
-// thread -> 4 output columns (21 column groups) x 4 rows (12 row groups).
-constexpr int kLinRows = 48;
+// Y[rows,84] = X[rows,84] * Wm[84,84] + b.  CTA = kLinRows rows, 252 active threads:
+// thread -> 4 output columns (21 column groups) x kLinIter rows (12 row groups).
+constexpr int kLinRows = 12;            // rows per CTA: 12 row groups x kLinIter rows (small CTAs: the two
+constexpr int kLinIter = kLinRows / 12;  // 84x84 linears are latency-bound, so spread them over >2 waves)
 
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) nl_linear_kernel(const float* __restrict__ X, int rows,
@@ -36,15 +37,15 @@ __global__ void __launch_bounds__(256) nl_linear_kernel(const float* __restrict_
   __syncthreads();
   if (tid >= 252) return;
   const int cgp = tid % 21, rg = tid / 21;
-  float acc[4][4];
+  float acc[kLinIter][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < kLinIter; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (int k = 0; k < kNL; ++k) {
     const float4 bv = *reinterpret_cast<const float4*>(wsm + k * kNL + cgp * 4);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kLinIter; ++i) {
       const int rl = rg + 12 * i;
       const float av = xsm[rl * kNL + k];
       acc[i][0] = fmaf(av, bv.x, acc[i][0]);
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(256) nl_linear_kernel(const float* __restrict_
   }
   const float4 bs = *reinterpret_cast<const float4*>(b + cgp * 4);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < kLinIter; ++i) {
     const int rl = rg + 12 * i;
     const long long row = (long long)row0 + rl;
     if (row >= rows) continue;
