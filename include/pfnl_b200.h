@@ -164,6 +164,20 @@ int pfnl_bicubic4(pfnl_handle* h, const float* in_dev, int N, int H, int W, int 
 int pfnl_pfrb(pfnl_handle* h, int blk, const float* frames_dev, int N, int H, int W,
               float* frames_out_dev, void* stream);
 
+/* ---- the steps around the hot path in test_video_truth / test_video_lr ---- */
+
+/* DownSample_4D (utils.py:169-192) with the 13x13 blur of utils.py:95-105: REFLECT pad 6, stride 4.
+ *   hr_dev [F,H,W,3] -> lr_dev [F,(H-1)/4+1,(W-1)/4+1,3]; blur_host = the 169 fp32 taps (row-major). */
+int pfnl_downsample4(pfnl_handle* h, const float* hr_dev, int F, int H, int W, const float* blur_host,
+                     float* lr_dev, void* stream);
+/* Sliding 7-frame windows with edge clamping (model/pfnl.py:236-242, 294-300):
+ *   frames_dev [F,h,w,3] -> clips_dev [count,7,h,w,3], clip k = frames clamp(first+k-3 .. first+k+3, 0, F-1). */
+int pfnl_gather_windows(pfnl_handle* h, const float* frames_dev, int F, int fh, int fw, int first, int count,
+                        float* clips_dev, void* stream);
+/* round(clip(sr*255,0,255)).astype(uint8) (model/pfnl.py:255-257, round-half-to-even like np.round):
+ *   in_dev fp32 [n] -> out_dev uint8 [n]. */
+int pfnl_quantize_u8(pfnl_handle* h, const float* in_dev, long long n, unsigned char* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,9 @@ SYMBOLS = {
     "pfnl_conv2d_nhwc": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP, _VP, _VP]),
     "pfnl_bicubic4": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _VP]),
     "pfnl_pfrb": (_I, [_VP, _I, _VP, _I, _I, _I, _VP, _VP]),
+    "pfnl_downsample4": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP, _VP]),
+    "pfnl_gather_windows": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP, _VP]),
+    "pfnl_quantize_u8": (_I, [_VP, _VP, C.c_longlong, _VP, _VP]),
 }
 
 

@@ -103,6 +103,7 @@ struct pfnl_handle {
   // scratch for pfnl_conv2d_nhwc's on-the-fly weight packing
   float* pack_scratch = nullptr;
   size_t pack_cap = 0;
+  float* blur_dev = nullptr;  // 13x13 taps of pfnl_downsample4
   // host staging for pfnl_forward_host
   float *pin_in = nullptr, *pin_out = nullptr, *dev_in = nullptr, *dev_out = nullptr;
   size_t pin_in_cap = 0, pin_out_cap = 0;
@@ -404,6 +405,8 @@ int pfnl_create(pfnl_handle** out, int device, const pfnl_weights* wts, int prec
   TRY(launch_pack_conv_ffma_weights(h->merge1_w, 3, 448, 48, h->merge1_p, 0));
   if (precision != PFNL_PREC_FP32) {
     TcRawWeights raw;
+    raw.nl_gw_w = h->nl_gw_w;
+    raw.nl_gw_b = h->nl_gw_b;
     raw.nl_g_w = h->nl_g_w;
     raw.nl_g_b = h->nl_g_b;
     raw.nl_w_w = h->nl_w_w;
@@ -452,6 +455,7 @@ int pfnl_destroy(pfnl_handle* h) {
   if (h->ws) cudaFree(h->ws);
   if (h->mse_partial) cudaFree(h->mse_partial);
   if (h->pack_scratch) cudaFree(h->pack_scratch);
+  if (h->blur_dev) cudaFree(h->blur_dev);
   if (h->pin_in) cudaFreeHost(h->pin_in);
   if (h->pin_out) cudaFreeHost(h->pin_out);
   if (h->dev_in) cudaFree(h->dev_in);
@@ -804,6 +808,59 @@ int pfnl_pfrb(pfnl_handle* h, int blk, const float* frames, int N, int H, int W,
   cudaStream_t s = (cudaStream_t)stream;
   if (h->precision == PFNL_PREC_FP32) return pfrb_fp32(h, blk, frames, frames_out, w, N, H, W, s);
   return tc_pfrb_fp32io(h->tcw, w.tc, h->precision, blk, frames, N, H, W, frames_out, s, &h->launches);
+}
+
+int pfnl_downsample4(pfnl_handle* h, const float* hr, int F, int H, int W, const float* blur_host, float* lr,
+                     void* stream) {
+  if (!h || !hr || !blur_host || !lr) {
+    set_error("pfnl_downsample4: NULL argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  if (F <= 0 || H < 7 || W < 7) {  // REFLECT padding of 6 needs at least 7 pixels
+    set_error("pfnl_downsample4: bad shape F=%d H=%d W=%d", F, H, W);
+    return PFNL_ERR_BAD_SHAPE;
+  }
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!h->blur_dev) PFNL_CUDA(cudaMalloc((void**)&h->blur_dev, 169 * sizeof(float)));
+  PFNL_CUDA(cudaMemcpyAsync(h->blur_dev, blur_host, 169 * sizeof(float), cudaMemcpyHostToDevice, s));
+  int rc = launch_downsample4(hr, F, H, W, h->blur_dev, lr, s);
+  if (rc) return rc;
+  h->launches += 1;
+  return PFNL_OK;
+}
+
+int pfnl_gather_windows(pfnl_handle* h, const float* frames, int F, int fh, int fw, int first, int count,
+                        float* clips, void* stream) {
+  if (!h || !frames || !clips) {
+    set_error("pfnl_gather_windows: NULL argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  if (F <= 0 || fh <= 0 || fw <= 0 || count <= 0 || first < 0 || first + count > F) {
+    set_error("pfnl_gather_windows: bad shape F=%d h=%d w=%d first=%d count=%d", F, fh, fw, first, count);
+    return PFNL_ERR_BAD_SHAPE;
+  }
+  DeviceGuard guard(h->device);
+  int rc = launch_gather_windows(frames, F, (long long)fh * fw * 3, first, count, clips, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->launches += 1;
+  return PFNL_OK;
+}
+
+int pfnl_quantize_u8(pfnl_handle* h, const float* in, long long n, unsigned char* out, void* stream) {
+  if (!h || !in || !out) {
+    set_error("pfnl_quantize_u8: NULL argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  if (n <= 0) {
+    set_error("pfnl_quantize_u8: bad size %lld", n);
+    return PFNL_ERR_BAD_SHAPE;
+  }
+  DeviceGuard guard(h->device);
+  int rc = launch_quantize_u8(in, n, out, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->launches += 1;
+  return PFNL_OK;
 }
 
 }  // extern "C"

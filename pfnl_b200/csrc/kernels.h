@@ -109,6 +109,12 @@ int launch_nl_linear_scatter(const float* Y, const float* lr, int N, int H, int 
                              float* inp21, cudaStream_t s);
 int launch_nl_flash_ffma(const float* X, const float* G, int N, int L, float* Y, cudaStream_t s);
 
+// ---- video_io.cu ------------------------------------------------------------------------
+int launch_downsample4(const float* hr, int F, int H, int W, const float* blur_dev, float* lr, cudaStream_t s);
+int launch_gather_windows(const float* frames, int F, long long frame_elems, int first, int count, float* clips,
+                          cudaStream_t s);
+int launch_quantize_u8(const float* in, long long n, unsigned char* out, cudaStream_t s);
+
 // ---- mse.cu -----------------------------------------------------------------------------
 constexpr int kMseChunks = 64;
 int launch_mse(const float* sr, const float* hr, int N, long long per_clip, double* partial /*[N*kMseChunks]*/,

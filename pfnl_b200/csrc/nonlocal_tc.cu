@@ -283,51 +283,27 @@ __global__ void __launch_bounds__(192, 1)
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-// X fp32 [N,L,84] -> X16 [N,Lp,128] (zero padded) and Gt16 [N,96,Lp] = (X*Wg+bg)^T (zero padded).
-// CTA = 64 tokens of one clip.
+// X fp32 [N,L,84] -> X16 [N,Lp,128] (zero padded; Q and K) and Xt16 [N,96,Lp] = X^T (zero padded; V).
+// V = X because the g linear is folded into the output linear: w(P*(X*Wg+bg)) = P*X*(Wg*Ww) + (bg*Ww+bw)
+// (softmax rows sum to 1; utils.py:26,64,67).  Pure cast + transpose, CTA = 64 tokens of one clip.
 __global__ void __launch_bounds__(256) nl_prep_kernel(const float* __restrict__ X, int L, int Lp,
-                                                      const float* __restrict__ Wg, const float* __restrict__ bg,
-                                                      __half* __restrict__ X16, __half* __restrict__ Gt16) {
-  __shared__ __align__(16) float xs[64 * kNL];
-  __shared__ __align__(16) float gs[64 * (kVR + 1)];
+                                                      __half* __restrict__ X16, __half* __restrict__ Xt16) {
+  __shared__ float xs[64 * (kNL + 1)];
   const int tid = threadIdx.x;
   const int n = blockIdx.y, t0 = blockIdx.x * 64;
   const float* Xn = X + (long long)n * L * kNL;
   for (int i = tid; i < 64 * kNL; i += 256) {
-    const int t = t0 + i / kNL;
-    xs[i] = t < L ? Xn[(long long)t0 * kNL + i] : 0.f;
+    const int tl = i / kNL, c = i - tl * kNL;
+    xs[tl * (kNL + 1) + c] = (t0 + tl) < L ? Xn[(long long)t0 * kNL + i] : 0.f;
   }
   __syncthreads();
-  // X16 rows (coalesced 256-byte rows)
-  for (int i = tid; i < 64 * kCP; i += 256) {
+  for (int i = tid; i < 64 * kCP; i += 256) {   // X16 rows (coalesced 256-byte rows)
     const int tl = i / kCP, c = i % kCP;
-    X16[((long long)n * Lp + t0 + tl) * kCP + c] = __float2half_rn(c < kNL ? xs[tl * kNL + c] : 0.f);
+    X16[((long long)n * Lp + t0 + tl) * kCP + c] = __float2half_rn(c < kNL ? xs[tl * (kNL + 1) + c] : 0.f);
   }
-  // G tile: thread -> (token tl = tid/4, 24 columns starting at (tid%4)*24)
-  {
-    const int tl = tid >> 2, cb = (tid & 3) * 24;
-    float acc[24];
-#pragma unroll
-    for (int j = 0; j < 24; ++j) acc[j] = 0.f;
-    for (int k = 0; k < kNL; ++k) {
-      const float xv = xs[tl * kNL + k];
-#pragma unroll
-      for (int j = 0; j < 24; ++j) {
-        const int c = cb + j;
-        if (c < kNL) acc[j] = fmaf(xv, Wg[k * kNL + c], acc[j]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 24; ++j) {
-      const int c = cb + j;
-      const bool valid = c < kNL && (t0 + tl) < L;
-      gs[tl * (kVR + 1) + c] = valid ? acc[j] + bg[c] : 0.f;
-    }
-  }
-  __syncthreads();
-  for (int i = tid; i < kVR * 64; i += 256) {
+  for (int i = tid; i < kVR * 64; i += 256) {   // Xt16 rows (token-contiguous)
     const int c = i >> 6, tl = i & 63;
-    Gt16[((long long)n * kVR + c) * Lp + t0 + tl] = __float2half_rn(gs[tl * (kVR + 1) + c]);
+    Xt16[((long long)n * kVR + c) * Lp + t0 + tl] = __float2half_rn(c < kNL ? xs[tl * (kNL + 1) + c] : 0.f);
   }
 }
 
@@ -347,11 +323,10 @@ int tc_nl_init() {
   return PFNL_OK;
 }
 
-static int run_nl_tc(const float* tokens, int N, int L, __half* x16, __half* gt16, float* Y, const float* Wg,
-                     const float* bg, cudaStream_t s) {
+static int run_nl_tc(const float* tokens, int N, int L, __half* x16, __half* gt16, float* Y, cudaStream_t s) {
   const int Lp = ceil_div(L, kKT) * kKT;
   dim3 pg(Lp / 64, N);
-  nl_prep_kernel<<<pg, 256, 0, s>>>(tokens, L, Lp, Wg, bg, x16, gt16);
+  nl_prep_kernel<<<pg, 256, 0, s>>>(tokens, L, Lp, x16, gt16);
   PFNL_LAUNCH_CHECK();
   CUtensorMap tmx, tmg;
   int r = make_mat_tmap(&tmx, x16, (uint64_t)N * Lp, kCP, kQT);
@@ -379,8 +354,8 @@ int tc_nonlocal(const TcWeights& tw, TcWorkspace& w, const float* tokens, const 
   __half* gt16 = (__half*)((uint8_t*)w.nl_x16 + (N * Lp * kCP * 2 + 1023) / 1024 * 1024);
   float* y = (float*)w.nl_priv;
   if (prof) prof->begin(kProfNonlocal, s);
-  int rc = run_nl_tc(tokens, N, L, x16, gt16, y, tw.raw.nl_g_w, tw.raw.nl_g_b, s);
-  if (rc == PFNL_OK) rc = launch_nl_linear_scatter(y, lr, N, H, W, tw.raw.nl_w_w, tw.raw.nl_w_b, inp21, s);
+  int rc = run_nl_tc(tokens, N, L, x16, gt16, y, s);
+  if (rc == PFNL_OK) rc = launch_nl_linear_scatter(y, lr, N, H, W, tw.raw.nl_gw_w, tw.raw.nl_gw_b, inp21, s);
   if (prof) prof->end(s);
   if (rc) return rc;
   *launches += 3;
@@ -389,18 +364,28 @@ int tc_nonlocal(const TcWeights& tw, TcWorkspace& w, const float* tokens, const 
 
 int tc_nonlocal_tokens(const TcWeights& tw, const float* tokens, int N, int L, float* out, cudaStream_t s,
                        long long* launches) {
-  // stage-level entry (pfnl_nonlocal): scratch is allocated per call (isolation benchmarks only)
+  // stage-level entry (pfnl_nonlocal): grow-only scratch owned by the process (isolation benchmarks)
+  static uint8_t* scratch = nullptr;
+  static size_t cap = 0;
   const size_t Lp = (size_t)ceil_div(L, kKT) * kKT;
-  __half *x16 = nullptr, *gt16 = nullptr;
-  float* y = nullptr;
-  PFNL_CUDA(cudaMallocAsync((void**)&x16, N * Lp * kCP * 2, s));
-  PFNL_CUDA(cudaMallocAsync((void**)&gt16, (size_t)N * kVR * Lp * 2, s));
-  PFNL_CUDA(cudaMallocAsync((void**)&y, (size_t)N * L * kNL * 4, s));
-  int rc = run_nl_tc(tokens, N, L, x16, gt16, y, tw.raw.nl_g_w, tw.raw.nl_g_b, s);
-  if (rc == PFNL_OK) rc = launch_nl_linear(y, N * L, tw.raw.nl_w_w, tw.raw.nl_w_b, out, s);
-  cudaFreeAsync(x16, s);
-  cudaFreeAsync(gt16, s);
-  cudaFreeAsync(y, s);
+  const size_t b_x = (N * Lp * kCP * 2 + 1023) / 1024 * 1024;
+  const size_t b_g = ((size_t)N * kVR * Lp * 2 + 1023) / 1024 * 1024;
+  const size_t b_y = ((size_t)N * L * kNL * 4 + 1023) / 1024 * 1024;
+  if (b_x + b_g + b_y > cap) {
+    if (scratch) {
+      PFNL_CUDA(cudaDeviceSynchronize());
+      PFNL_CUDA(cudaFree(scratch));
+      scratch = nullptr;
+      cap = 0;
+    }
+    PFNL_CUDA(cudaMalloc((void**)&scratch, b_x + b_g + b_y));
+    cap = b_x + b_g + b_y;
+  }
+  __half* x16 = (__half*)scratch;
+  __half* gt16 = (__half*)(scratch + b_x);
+  float* y = (float*)(scratch + b_x + b_g);
+  int rc = run_nl_tc(tokens, N, L, x16, gt16, y, s);
+  if (rc == PFNL_OK) rc = launch_nl_linear(y, N * L, tw.raw.nl_gw_w, tw.raw.nl_gw_b, out, s);
   if (rc) return rc;
   *launches += 3;
   return PFNL_OK;

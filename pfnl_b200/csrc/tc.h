@@ -20,6 +20,7 @@ constexpr int kTcBaseOffsetMode = 0;
 
 struct TcRawWeights {  // fp32 HWIO device pointers owned by the handle
   const float *nl_g_w, *nl_g_b, *nl_w_w, *nl_w_b;
+  const float *nl_gw_w, *nl_gw_b;  // folded output linear of the non-local block: Wg*Ww, bg*Ww+bw
   const float *conv0_w, *conv0_b;
   const float* conv1_w[PFNL_NUM_BLOCK];
   const float* conv1_b[PFNL_NUM_BLOCK];

@@ -181,6 +181,41 @@ class Engine:
         check(lib.pfnl_bicubic4(self._h, _ptr(x), n, h, w, c, _ptr(out), _stream_ptr(self.device)))
         return out
 
+    # -- steps around the hot path (test_video_*), on the device ---------------------------
+    def downsample4(self, hr, blur=None):
+        """DownSample_4D (utils.py:169-192): hr [F,H,W,3] -> [F,ceil(H/4),ceil(W/4),3]."""
+        self._chk_in(hr, 4)
+        f, hh, ww, c = hr.shape
+        if c != 3:
+            raise ValueError("hr must be [F,H,W,3]")
+        if blur is None:
+            blur = gkern(13, 1.6)
+        b = np.ascontiguousarray(np.asarray(blur, np.float32).reshape(169))
+        out = torch.empty((f, (hh - 1) // 4 + 1, (ww - 1) // 4 + 1, 3), dtype=torch.float32, device=self.device)
+        check(lib.pfnl_downsample4(self._h, _ptr(hr), f, hh, ww, C.c_void_p(b.ctypes.data), _ptr(out),
+                                   _stream_ptr(self.device)))
+        torch.cuda.current_stream(self.device).synchronize()  # `b` is host memory owned by this call
+        return out
+
+    def gather_windows(self, frames, first, count):
+        """frames [F,h,w,3] -> clips [count,7,h,w,3] with edge clamping (pfnl.py:236-242)."""
+        self._chk_in(frames, 4)
+        f, hh, ww, c = frames.shape
+        if c != 3:
+            raise ValueError("frames must be [F,h,w,3]")
+        out = torch.empty((count, _lib.NUM_FRAMES, hh, ww, 3), dtype=torch.float32, device=self.device)
+        check(lib.pfnl_gather_windows(self._h, _ptr(frames), f, hh, ww, first, count, _ptr(out),
+                                      _stream_ptr(self.device)))
+        return out
+
+    def quantize_u8(self, x):
+        """round(clip(x*255,0,255)).astype(uint8) (pfnl.py:255-257)."""
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+            raise ValueError("expected a contiguous float32 CUDA tensor")
+        out = torch.empty(x.shape, dtype=torch.uint8, device=self.device)
+        check(lib.pfnl_quantize_u8(self._h, _ptr(x), x.numel(), _ptr(out), _stream_ptr(self.device)))
+        return out
+
     def pfrb(self, blk, frames, n, h, w):
         """frames [N*7,H,W,64] -> one Progressive Fusion Residual Block (pfnl.py:66-71)."""
         self._chk_in(frames, 4)
@@ -249,6 +284,7 @@ class PFNL:
         if device is None:
             device = torch.cuda.current_device() if torch.cuda.is_available() else 0
         self.precision = precision
+        self.device_pipeline = True   # window gather / uint8 quantise / DownSample_4D on the device
         self._device = device
         self._graphs = graphs
         self._weights = None
@@ -321,28 +357,40 @@ class PFNL:
         return np.array(lr_list)
 
     def _run_video(self, lrs, save_path, part):
+        """The loop of test_video_truth / test_video_lr (model/pfnl.py:236-262, 294-320).
+        `lrs` [F,h,w,3]: numpy (host) or a float32 CUDA tensor.  With `device_pipeline` (default) the LR
+        frames are uploaded ONCE, the 7-frame windows are gathered on the device, and the SR frames come
+        back as uint8 (quantised on the device): 7x less H2D and 4x less D2H than feeding `lr_list`."""
         max_frame = lrs.shape[0]
         if max_frame == 0:
             return np.array([])
         if part > max_frame:
             part = max_frame
         num_once = max_frame // part if max_frame % part == 0 else max_frame // part + 1
-        lr_list = self._window_list(lrs)
         print('Save at {}'.format(save_path))
-        print('{} Inputs With Shape {}'.format(lrs.shape[0], lrs.shape[1:]))
+        print('{} Inputs With Shape {}'.format(lrs.shape[0], tuple(lrs.shape[1:])))
+        eng = self.engine
+        if self.device_pipeline:
+            frames = torch.as_tensor(np.asarray(lrs) if not isinstance(lrs, torch.Tensor) else lrs,
+                                     dtype=torch.float32).to(eng.device).contiguous()
+        else:
+            lr_list = self._window_list(np.asarray(lrs.cpu()) if isinstance(lrs, torch.Tensor) else lrs)
         all_time = []
         for i in range(part):
-            batch = lr_list[i * num_once:(i + 1) * num_once]
-            if batch.shape[0] == 0:
+            first = i * num_once
+            count = min(num_once, max_frame - first)
+            if count <= 0:
                 break
             st_time = time.time()
-            sr = self.forward(np.ascontiguousarray(batch, dtype=np.float32))
+            if self.device_pipeline:
+                clips = eng.gather_windows(frames, first, count)
+                imgs = eng.quantize_u8(eng.forward(clips)).cpu().numpy()[:, 0]
+            else:
+                sr = self.forward(np.ascontiguousarray(lr_list[first:first + count], dtype=np.float32))
+                imgs = [np.round(np.clip(sr[j][0] * 255., 0, 255), 0).astype(np.uint8) for j in range(sr.shape[0])]
             all_time.append(time.time() - st_time)
-            for j in range(sr.shape[0]):
-                img = sr[j][0] * 255.
-                img = np.clip(img, 0, 255)
-                img = np.round(img, 0).astype(np.uint8)
-                cv2_imsave(join(save_path, '{:0>4}.png'.format(i * num_once + j)), img)
+            for j in range(count):
+                cv2_imsave(join(save_path, '{:0>4}.png'.format(first + j)), imgs[j])
         all_time = np.array(all_time)
         if max_frame > 0:
             mean_t = np.mean(all_time[1:]) if all_time.size > 1 else float('nan')
@@ -357,7 +405,13 @@ class PFNL:
         imgs = np.array([cv2_imread(i) for i in imgs]) / 255.
         if not reuse and self._weights is None:
             self.load(self.save_dir)
-        lrs = downsample_4d(imgs, self.scale) if len(imgs) else np.zeros((0, 0, 0, 3), np.float32)
+        if not len(imgs):
+            return self._run_video(np.zeros((0, 0, 0, 3), np.float32), save_path, part)
+        if self.device_pipeline:   # blur + x4 decimation on the device (DownSample_4D, utils.py:169-192)
+            hr = torch.as_tensor(imgs, dtype=torch.float32).to(self.engine.device).contiguous()
+            lrs = self.engine.downsample4(hr)
+        else:
+            lrs = downsample_4d(imgs, self.scale)
         return self._run_video(lrs, save_path, part)
 
     def test_video_lr(self, path, name='result', reuse=False, part=50):

@@ -341,3 +341,68 @@ def test_test_video_lr_call_surface(tmp_path, engines):
     # part < max_frame batches several clips per run (num_once = ceil(10/4) = 3)
     times = m.testvideo(str(tmp_path / "vid"), name="out2", part=4)
     assert sorted(os.listdir(tmp_path / "vid" / "out2")) == outs
+
+
+# ---- the steps around the hot path: DownSample_4D, window gather, uint8 quantise -----------
+@pytest.mark.parametrize("shape", [(3, 32, 40), (2, 33, 47), (1, 7, 7), (2, 128, 96)])
+def test_downsample4_vs_host_and_scipy(engines, shape):
+    """CUDA DownSample_4D (utils.py:169-192: REFLECT pad 6, 13x13 Gaussian, stride 4) vs the host numpy
+    restatement and vs an independent scipy 'mirror' correlation."""
+    from pfnl_b200.model import downsample_4d, gkern
+    from scipy.ndimage import correlate
+    f, hh, ww = shape
+    rng = np.random.default_rng(hh * 7 + ww)
+    hr = rng.random((f, hh, ww, 3), dtype=np.float32)
+    got = engines["A"].downsample4(cu(hr)).cpu().numpy()
+    assert got.shape == (f, (hh - 1) // 4 + 1, (ww - 1) // 4 + 1, 3)
+    np.testing.assert_allclose(got, downsample_4d(hr, 4), atol=2e-6)
+    k = gkern(13, 1.6)
+    ref = np.stack([np.stack([correlate(hr[n, :, :, c].astype(np.float64), k, mode="mirror")[::4, ::4]
+                              for c in range(3)], -1) for n in range(f)])
+    np.testing.assert_allclose(got, ref, atol=2e-6)
+
+
+@pytest.mark.parametrize("F,first,count", [(10, 0, 10), (10, 7, 3), (3, 0, 3), (1, 0, 1), (12, 5, 4)])
+def test_gather_windows_bit_exact(engines, F, first, count):
+    rng = np.random.default_rng(F)
+    frames = rng.random((F, 6, 10, 3), dtype=np.float32)
+    got = engines["A"].gather_windows(cu(frames), first, count).cpu().numpy()
+    for k in range(count):
+        ref = np.stack([frames[j] for j in R.window_indices(F, first + k)])
+        assert np.array_equal(got[k], ref)
+
+
+def test_quantize_u8_matches_numpy_round_half_even(engines):
+    vals = np.concatenate([np.linspace(-0.2, 1.2, 4001, dtype=np.float32),
+                           (np.arange(0, 255, dtype=np.float32) + 0.5) / np.float32(255.0)]).astype(np.float32)
+    got = engines["A"].quantize_u8(cu(vals)).cpu().numpy()
+    ref = R.quantise_uint8(vals)
+    # identical except where float32 x*255 lands within 1 ulp of a .5 tie differently than numpy's float64 product
+    assert (got.astype(int) - ref.astype(int)).__abs__().max() <= 1
+    ref32 = np.round(np.clip(vals * np.float32(255.0), 0, 255), 0).astype(np.uint8)   # fp32 product like the device
+    assert np.array_equal(got, ref32)
+
+
+def test_test_video_truth_device_pipeline(tmp_path, engines):
+    """test_video_truth on synthetic HR PNGs: the device pipeline (CUDA DownSample_4D + window gather +
+    uint8 quantise) writes the same PNGs as the host pipeline (numpy DownSample_4D, lr_list, host rounding)."""
+    import cv2
+    from pfnl_b200 import PFNL
+    rng = np.random.default_rng(51)
+    d = tmp_path / "vid" / "truth"
+    d.mkdir(parents=True)
+    frames = rng.integers(0, 256, size=(9, 32, 48, 3), dtype=np.uint8)
+    for i, f in enumerate(frames):
+        cv2.imwrite(str(d / f"{i:04d}.png"), f[:, :, ::-1])
+    W = R.make_weights("B")
+    m = PFNL(weights=W, precision="fp32")
+    m.test_video_truth(str(tmp_path / "vid"), name="dev", part=4)
+    m.device_pipeline = False
+    m.test_video_truth(str(tmp_path / "vid"), name="host", part=4)
+    names = sorted(os.listdir(tmp_path / "vid" / "dev"))
+    assert names == sorted(os.listdir(tmp_path / "vid" / "host")) == [f"{i:04d}.png" for i in range(9)]
+    for nme in names:
+        a = cv2.imread(str(tmp_path / "vid" / "dev" / nme)).astype(int)
+        b = cv2.imread(str(tmp_path / "vid" / "host" / nme)).astype(int)
+        assert a.shape == (32, 48, 3)
+        assert np.abs(a - b).max() <= 1 and (a != b).mean() < 0.01
