@@ -180,6 +180,11 @@ __device__ __forceinline__ void st256(void* ptr, const U256& r) {
                "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]), "r"(r.w[7])
                : "memory");
 }
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -521,6 +526,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const uint32_t tmem = ctl->tmem_base;
   pdl_launch_dependents();  // let the next kernel's CTAs start their prologue as SMs free up
   pdl_wait();               // activations written by the previous kernel are visible after this
+  if (cm.trace != nullptr && tid == 0) cm.trace[192 + 2 * blockIdx.x] = globaltimer_ns();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -591,6 +597,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, KC::TMEM_COLS);
+  if (cm.trace != nullptr && tid == 0) cm.trace[193 + 2 * blockIdx.x] = globaltimer_ns();
   if (cs > 1) cluster_sync_all();  // no CTA leaves while a peer's multicast may still target the cluster
 }
 
@@ -839,14 +846,14 @@ int launch_tc(const TcProgram& prog, int nphases, bool phase1_reads_phase0, int 
   static long long* trace_dev = nullptr;
   static const bool tracing = getenv("PFNL_TC_TRACE") != nullptr;
   if (tracing) {
-    if (!trace_dev) PFNL_CUDA(cudaMalloc((void**)&trace_dev, 3 * 64 * sizeof(long long)));
-    PFNL_CUDA(cudaMemsetAsync(trace_dev, 0, 3 * 64 * sizeof(long long), s));
+    if (!trace_dev) PFNL_CUDA(cudaMalloc((void**)&trace_dev, (192 + 2 * 256) * sizeof(long long)));
+    PFNL_CUDA(cudaMemsetAsync(trace_dev, 0, (192 + 2 * 256) * sizeof(long long), s));
     cm.trace = trace_dev;
   }
   const TcPhase& bb = prog.ph[nphases > 1 ? 1 : 0];
   PFNL_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<P0, P1, NSPLIT>, prog, cm));
   if (tracing) {
-    long long t[3 * 64];
+    long long t[192 + 2 * 256];
     PFNL_CUDA(cudaStreamSynchronize(s));
     PFNL_CUDA(cudaMemcpy(t, trace_dev, sizeof(t), cudaMemcpyDeviceToHost));
     const long long t0 = t[0];
@@ -864,6 +871,23 @@ int launch_tc(const TcProgram& prog, int nphases, bool phase1_reads_phase0, int 
     for (int i = 0; i < 12 && t[128 + 2 * i]; ++i)
       fprintf(stderr, " (%lld,%lld)", t[128 + 2 * i] - t0, t[128 + 1 + 2 * i] - t0);
     fprintf(stderr, "\n");
+    // per-CTA wall clock (globaltimer, ns): when each CTA passed the dependency wait and when it finished
+    long long smin = 0, smax = 0, emin = 0, emax = 0, dmin = 0, dmax = 0, dsum = 0;
+    for (int b = 0; b < grid && b < 256; ++b) {
+      const long long st = t[192 + 2 * b], en = t[193 + 2 * b], d = en - st;
+      if (b == 0 || st < smin) smin = st;
+      if (b == 0 || st > smax) smax = st;
+      if (b == 0 || en < emin) emin = en;
+      if (b == 0 || en > emax) emax = en;
+      if (b == 0 || d < dmin) dmin = d;
+      if (b == 0 || d > dmax) dmax = d;
+      dsum += d;
+    }
+    fprintf(stderr,
+            "  per-CTA: start spread %.2f us, end spread %.2f us, CTA duration min/avg/max %.2f/%.2f/%.2f us, "
+            "kernel span (first start -> last end) %.2f us\n",
+            (smax - smin) / 1e3, (emax - emin) / 1e3, dmin / 1e3, dsum / 1e3 / (grid < 256 ? grid : 256), dmax / 1e3,
+            (emax - smin) / 1e3);
   }
   return PFNL_OK;
 }
