@@ -1,8 +1,14 @@
 // Tensor-core convolutions of the PFRB stack (model/pfnl.py:65-74) for sm_100a:
 // TMA -> shared memory -> tcgen05.mma (fp16 operands, fp32 accumulators in TMEM) -> fused epilogue.
 //
-// Data layout in HBM: activations are fp16 NHWC planes [images, H, W, 64] (one pixel = one
-// 128-byte row = one 128B-swizzle row).  PFNL_PREC_TC_FP16 keeps one plane per tensor;
+// Data layout in HBM: activations are fp16 planes stored channel-chunk-major,
+// [images][8 chunks][H][W][8 ch]: an epilogue warp owns 32 pixels (4 tile rows x 8) x 16 channels, so
+// with this layout each of its 16-byte-per-lane accesses covers 4 runs of 128 contiguous bytes (4 L1
+// wavefronts per instruction, every byte of every line used) instead of touching 32 different
+// 128-byte lines for 32 bytes each as pixel-major NHWC rows do.  The L1/shared-memory data path is
+// the shared resource of this kernel - the UMMA operand reads alone keep it ~90 % busy - so epilogue
+// wavefronts cost tile time one for one (ncu: l1tex 53 % with the NHWC layout, profiles/r10_*).
+// PFNL_PREC_TC_FP16 keeps one plane per tensor;
 // PFNL_PREC_TC_FP16X3 keeps two (hi = fp16(v), lo = fp16((v-hi)*2048)) and computes
 //   [D0 | D1] += A_hi x [W_hi ; W_lo]   (one N = 128 MMA per k-step: one A read for two products)
 //        D1   += A_lo x  W_hi           (N = 64)
@@ -12,12 +18,13 @@
 //
 // Implicit GEMM: M = 128 output pixels (a 16-row x 8-column spatial tile of one image),
 // N = 64 (48 for convmerge1) output channels, K = taps x 64 input channels.  Per tile ONE TMA
-// box {64 ch, 10 px, 18 rows} (out-of-bounds zero fill == 'same' zero padding) lands a halo
-// patch in smem; the A operand of tap (dy,dx) is the same patch addressed through a UMMA
-// descriptor whose start is shifted by (dy*10+dx) 128-byte rows and whose 8-row-group stride
-// (SBO) is 10*128 - each input byte is fetched from L2 once per tile, not 9 times.  (The 128B
-// swizzle is a function of the absolute smem address on B200: shifted windows need no padding and
-// base_offset = 0, and they run at the same MMA rate as standard tiles; probes/.)
+// box {10 px x 8 ch, 18 rows, 8 chunks} (out-of-bounds zero fill == 'same' zero padding) lands a
+// halo patch in smem as 8 sub-patches of [18][10] 16-byte pixels, un-swizzled: 8 consecutive pixels
+// of a row are one UMMA core matrix (8 rows x 16 B, contiguous).  The A operand of tap (dy,dx),
+// k-step k is sub-patches 2k, 2k+1 (LBO = sub-patch size) addressed through a descriptor whose
+// start is shifted by (dy*10+dx) pixels and whose 8-row-group stride (SBO) is one patch row (10
+// pixels) - each input byte is fetched from L2 once per tile, not 9 times, and no alignment or
+// swizzle phase constrains the shift.
 // Weights ([taps][N][64] fp16, pre-swizzled) are resident in smem while a phase runs.
 //
 // One launch runs up to two PHASES back to back on the same persistent CTAs, swapping the weight
@@ -60,8 +67,9 @@ struct TcPhase {
   int img_mul, img_add;      // source image coordinate of stage s = out_img*img_mul + img_add + s
   int epi;
   int accumulate;            // kEpiPartialF32: add the previous content of out_f32
+  int f32_chunked;           // out_f32 is chunk-major [img][4][H][W][16] (the conv2 partial sums) instead of NHWC
   const float* bias;         // [NOUT] or NULL
-  const float* pbase;        // fp32 [out_img/frames][H][W][64] (kEpiResPlanes)
+  const float* pbase;        // fp32 [out_img/frames][4][H][W][16], channel-chunk-major (kEpiResPlanes)
   __half* out_hi;
   __half* out_lo;
   const __half* res_hi;
@@ -146,6 +154,15 @@ __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
   lo = __float2half_rn((v - __half2float(hi)) * 2048.f);
 }
 
+// element offset of (image, 8-channel chunk, y, x) in a channel-chunk-major fp16 plane [img][8][H][W][8]
+__device__ __forceinline__ long long plane_off(int img, int chunk8, int y, int x, int H, int W) {
+  return ((((long long)img * 8 + chunk8) * H + y) * W + x) * 8;
+}
+// fp32 partial sums of conv2's base half: [img][4 chunks][H][W][16] (64 contiguous bytes per thread)
+__device__ __forceinline__ long long pbase_off(int img, int chunk16, int y, int x, int H, int W) {
+  return ((((long long)img * 4 + chunk16) * H + y) * W + x) * 16;
+}
+
 // accumulation chain of tap tp (3x3: taps 0-4 -> chain 0, 5-8 -> chain 1 when NCH = 2) or source s
 template <int KS, int NCH>
 __device__ __forceinline__ constexpr int tc_chain(int tp, int s) {
@@ -179,6 +196,20 @@ __device__ __forceinline__ void st256(void* ptr, const U256& r) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(r.w[0]), "r"(r.w[1]), "r"(r.w[2]),
                "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]), "r"(r.w[7])
                : "memory");
+}
+// one fp16 plane access of an epilogue thread: its 16 channels = two 16-byte pieces, `cs` elements apart
+// (cs = H*W*8, the chunk stride of the plane)
+__device__ __forceinline__ U256 ld_plane16(const __half* p, long long cs) {
+  U256 r;
+  const uint4 a = *reinterpret_cast<const uint4*>(p);
+  const uint4 b = *reinterpret_cast<const uint4*>(p + cs);
+  r.w[0] = a.x, r.w[1] = a.y, r.w[2] = a.z, r.w[3] = a.w;
+  r.w[4] = b.x, r.w[5] = b.y, r.w[6] = b.z, r.w[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void st_plane16(__half* p, long long cs, const U256& r) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]);
+  *reinterpret_cast<uint4*>(p + cs) = make_uint4(r.w[4], r.w[5], r.w[6], r.w[7]);
 }
 __device__ __forceinline__ long long globaltimer_ns() {
   long long t;
@@ -232,8 +263,8 @@ __device__ __forceinline__ void producer_phase(const TcPhase& P, const TcCommon&
           const int fimg = (fr / cm.tiles_y) * P.frames + ft;
           for (int s = 0; s < PC::NSRC; ++s) {
             const int fic = fimg * P.img_mul + P.img_add + s;
-            tma_prefetch_4d(&P.tm_hi, 0, ftx * 8 - PAD, fty * 16 - PAD, fic);
-            if (NSPLIT == 2) tma_prefetch_4d(&P.tm_lo, 0, ftx * 8 - PAD, fty * 16 - PAD, fic);
+            tma_prefetch_4d(&P.tm_hi, (ftx * 8 - PAD) * 8, fty * 16 - PAD, 0, fic);
+            if (NSPLIT == 2) tma_prefetch_4d(&P.tm_lo, (ftx * 8 - PAD) * 8, fty * 16 - PAD, 0, fic);
           }
         }
       }
@@ -243,7 +274,8 @@ __device__ __forceinline__ void producer_phase(const TcPhase& P, const TcCommon&
         for (int pl = 0; pl < NSPLIT; ++pl) {  // hi plane first (consumed first), then lo
           mbar_wait(&ctl->empty[rg.sl], rg.ph ^ 1);
           mbar_arrive_expect_tx(&ctl->full[rg.sl], PC::PATCH_BYTES);
-          tma_load_4d(ring + rg.sl * KC::SLOT_BYTES, pl == 1 ? &P.tm_lo : &P.tm_hi, &ctl->full[rg.sl], 0, x0, y0, ic);
+          tma_load_4d(ring + rg.sl * KC::SLOT_BYTES, pl == 1 ? &P.tm_lo : &P.tm_hi, &ctl->full[rg.sl], x0 * 8, y0, 0,
+                      ic);
           if (++rg.sl == KC::NS) {
             rg.sl = 0;
             rg.ph ^= 1;
@@ -261,7 +293,10 @@ __device__ __forceinline__ void mma_phase(const TcPhase& P, const TcCommon& cm, 
   constexpr int TAP_BYTES = NSPLIT * PC::WT_BYTES;
   constexpr uint32_t idesc_lo = make_idesc_f16(128, NOUT);           // A_lo x W_hi          -> D1
   constexpr uint32_t idesc_hi = make_idesc_f16(128, NSPLIT * NOUT);  // A_hi x [W_hi ; W_lo] -> [D0 | D1]
-  constexpr uint32_t SBO_A = PC::BOX_W * 128;
+  // A operand (un-swizzled K-major): pixels of 16 B per 8-channel sub-patch; an 8-pixel tile row is one core
+  // matrix, consecutive tile rows are one patch row apart (SBO), the two k-chunks one sub-patch apart (LBO)
+  constexpr uint32_t SBO_A = PC::BOX_W * 16;
+  constexpr uint32_t SUB_A = PC::BOX_W * PC::BOX_H * 16;  // bytes per sub-patch
   const uint64_t wd = make_sdesc_sw128(smem_u32(wsm), 1024, 0);
   for (int u = blockIdx.x; u < P.n_units; u += gridDim.x)
     for (int t = 0; t < P.frames; ++t, ++it) {
@@ -277,7 +312,7 @@ __device__ __forceinline__ void mma_phase(const TcPhase& P, const TcCommon& cm, 
         fence_after_sync();
         if (lane == 0 && s == 0) TC_TRACE(1, 1 + 2 * it);
         {
-          const uint64_t ad = make_sdesc_sw128(smem_u32(ring + rg.sl * KC::SLOT_BYTES), SBO_A, 0);
+          const uint64_t ad = make_sdesc_interleave(smem_u32(ring + rg.sl * KC::SLOT_BYTES), SUB_A, SBO_A);
           if (elect_one()) {
             uint32_t am = accmask;
 #pragma unroll
@@ -285,7 +320,7 @@ __device__ __forceinline__ void mma_phase(const TcPhase& P, const TcCommon& cm, 
               const int ch = tc_chain<KS, NCH>(tp, s);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint32_t aoff = (((tp / KS) * PC::BOX_W + (tp % KS)) * 128 + k * 32) >> 4;
+                const uint32_t aoff = (((tp / KS) * PC::BOX_W + (tp % KS)) * 16 + k * 2 * SUB_A) >> 4;
                 const uint32_t boff = (tp * TAP_BYTES + k * 32) >> 4;
                 mma_f16(dbase + ch * KC::CH_STRIDE, ad + aoff, wsd + boff, idesc_hi, (am >> ch) & 1u);
                 am |= 1u << ch;
@@ -307,13 +342,13 @@ __device__ __forceinline__ void mma_phase(const TcPhase& P, const TcCommon& cm, 
           //      tap 0 / source 0 always belongs to chain 0), so this always accumulates
           mbar_wait(&ctl->full[rg.sl], rg.ph);
           fence_after_sync();
-          const uint64_t ad = make_sdesc_sw128(smem_u32(ring + rg.sl * KC::SLOT_BYTES), SBO_A, 0);
+          const uint64_t ad = make_sdesc_interleave(smem_u32(ring + rg.sl * KC::SLOT_BYTES), SUB_A, SBO_A);
           if (elect_one()) {
 #pragma unroll
             for (int tp = 0; tp < TAPS; ++tp) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint32_t aoff = (((tp / KS) * PC::BOX_W + (tp % KS)) * 128 + k * 32) >> 4;
+                const uint32_t aoff = (((tp / KS) * PC::BOX_W + (tp % KS)) * 16 + k * 2 * SUB_A) >> 4;
                 const uint32_t boff = (tp * TAP_BYTES + k * 32) >> 4;
                 mma_f16(dbase + NOUT, ad + aoff, wsd + boff, idesc_lo, 1u);
               }
@@ -358,6 +393,9 @@ __device__ __forceinline__ void epilogue_phase(const TcPhase& P, const TcCommon&
       const int y = ty * 16 + my, x = tx * 8 + mx;
       const bool inb = chunk_active && y < cm.H && x < cm.W;
       const long long pix = ((long long)img * cm.H + y) * cm.W + x;
+      const long long poff = plane_off(img, c0 >> 3, y, x, cm.H, cm.W);  // this thread's first 8 channels in a plane
+      const long long cs = (long long)cm.H * cm.W * 8;                    // ... the other 8 are one chunk further
+      const long long foff = pbase_off(img, c0 >> 4, y, x, cm.H, cm.W);
       // ---- prefetch (independent of the accumulator) ----
       U256 rh, rl;
 #pragma unroll
@@ -365,14 +403,14 @@ __device__ __forceinline__ void epilogue_phase(const TcPhase& P, const TcCommon&
       if (inb) {
         if (epi_res) {
           if (t == 0) {  // the base-half partial sums are shared by the unit's 7 frames: load once
-            const float* pb = P.pbase + (((long long)nimg * cm.H + y) * cm.W + x) * 64 + c0;
+            const float* pb = P.pbase + pbase_off(nimg, c0 >> 4, y, x, cm.H, cm.W);
             pre[0] = ld256(pb);
             pre[1] = ld256(pb + 8);
           }
-          rh = ld256(P.res_hi + pix * 64 + c0);
-          if (NSPLIT == 2) rl = ld256(P.res_lo + pix * 64 + c0);
+          rh = ld_plane16(P.res_hi + poff, cs);
+          if (NSPLIT == 2) rl = ld_plane16(P.res_lo + poff, cs);
         } else if (epi_prev) {
-          const float* o = P.out_f32 + pix * NOUT + c0;
+          const float* o = P.out_f32 + (P.f32_chunked ? foff : pix * NOUT + c0);
           pre[0] = ld256(o);
           pre[1] = ld256(o + 8);
         }
@@ -441,8 +479,8 @@ __device__ __forceinline__ void epilogue_phase(const TcPhase& P, const TcCommon&
             else
               ph[j] = __float2half_rn(v[j]);
           }
-          st256(P.out_hi + pix * 64 + c0, oh);
-          if (NSPLIT == 2) st256(P.out_lo + pix * 64 + c0, ol);
+          st_plane16(P.out_hi + poff, cs, oh);
+          if (NSPLIT == 2) st_plane16(P.out_lo + poff, cs, ol);
         } else {
           if (P.epi == kEpiFinalF32) {
 #pragma unroll
@@ -454,7 +492,7 @@ __device__ __forceinline__ void epilogue_phase(const TcPhase& P, const TcCommon&
             o0.w[j] = __float_as_uint(v[j]);
             o1.w[j] = __float_as_uint(v[8 + j]);
           }
-          float* o = P.out_f32 + pix * NOUT + c0;
+          float* o = P.out_f32 + (P.f32_chunked ? foff : pix * NOUT + c0);
           st256(o, o0);
           st256(o + 8, o1);
         }
@@ -625,26 +663,33 @@ __global__ void pack_tc_weights_kernel(const float* __restrict__ hwio, int taps,
   }
 }
 
-// fp32 NHWC [.., 64] <-> fp16 planes
-__global__ void f32_to_planes_kernel(const float* __restrict__ in, long long n, int nsplit, __half* __restrict__ hi,
-                                     __half* __restrict__ lo) {
+// fp32 NHWC [images*H*W, 64] <-> fp16 planes (channel-chunk-major); hw = H*W
+__device__ __forceinline__ long long plane_index(long long e, long long hw) {
+  const int c = (int)(e & 63);
+  const long long pix = e >> 6, img = pix / hw, p = pix - img * hw;
+  return ((img * 8 + (c >> 3)) * hw + p) * 8 + (c & 7);
+}
+__global__ void f32_to_planes_kernel(const float* __restrict__ in, long long n, long long hw, int nsplit,
+                                     __half* __restrict__ hi, __half* __restrict__ lo) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     const float v = in[e];
+    const long long o = plane_index(e, hw);
     if (nsplit == 2) {
       __half h, l;
       split_half(v, h, l);
-      hi[e] = h;
-      lo[e] = l;
+      hi[o] = h;
+      lo[o] = l;
     } else {
-      hi[e] = __float2half_rn(v);
+      hi[o] = __float2half_rn(v);
     }
   }
 }
 __global__ void planes_to_f32_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, long long n,
-                                     int nsplit, float* __restrict__ out) {
+                                     long long hw, int nsplit, float* __restrict__ out) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-    float v = __half2float(hi[e]);
-    if (nsplit == 2) v = fmaf(__half2float(lo[e]), 1.f / 2048.f, v);
+    const long long o = plane_index(e, hw);
+    float v = __half2float(hi[o]);
+    if (nsplit == 2) v = fmaf(__half2float(lo[o]), 1.f / 2048.f, v);
     out[e] = v;
   }
 }
@@ -726,7 +771,8 @@ __global__ void __launch_bounds__(256, 2) conv0_planes_kernel(const float* __res
     for (int i = 0; i < 4; ++i) {
       const int gx = x0 + px0 + i;
       if (gx >= W) continue;
-      const long long pix = ((long long)img * H + gy) * W + gx;
+      const long long poff = plane_off(img, g * 2, gy, gx, H, W);
+      const long long cs = (long long)H * W * 8;
       U256 oh, ol;
       __half* ph = reinterpret_cast<__half*>(&oh);
       __half* pl = reinterpret_cast<__half*>(&ol);
@@ -738,8 +784,8 @@ __global__ void __launch_bounds__(256, 2) conv0_planes_kernel(const float* __res
         else
           ph[j] = __float2half_rn(v);
       }
-      st256(out_hi + pix * 64 + g * 16, oh);
-      if (NSPLIT == 2) st256(out_lo + pix * 64 + g * 16, ol);
+      st_plane16(out_hi + poff, cs, oh);
+      if (NSPLIT == 2) st_plane16(out_lo + poff, cs, ol);
     }
   }
 }
@@ -1057,6 +1103,7 @@ int pfrb_tc(const TcWeights& tw, TcWorkspace& w, int i, int N, int H, int W, cud
   a.n_units = units;
   a.img_mul = 1;
   a.epi = kEpiPartialF32;
+  a.f32_chunked = 1;
   a.out_f32 = w.pbase;
   if ((rc = phase_sources<typename SH::C3>(b, w.actB[0], w.actB[1], N * kFrames, H, W))) return rc;
   b.wimg = (const __half*)tw.conv2f[i];
@@ -1131,12 +1178,14 @@ int tc_pfrb_fp32io(const TcWeights& tw, TcWorkspace& w, int precision, int blk, 
                    int W, float* frames_out, cudaStream_t s, long long* launches) {
   const int ns = precision == PFNL_PREC_TC_FP16X3 ? 2 : 1;
   const long long n = (long long)N * kFrames * H * W * 64;
-  f32_to_planes_kernel<<<148 * 8, 256, 0, s>>>(frames, n, ns, (__half*)w.actA[0], (__half*)w.actA[1]);
+  f32_to_planes_kernel<<<148 * 8, 256, 0, s>>>(frames, n, (long long)H * W, ns, (__half*)w.actA[0],
+                                               (__half*)w.actA[1]);
   PFNL_LAUNCH_CHECK();
   int rc = ns == 2 ? pfrb_tc<2>(tw, w, blk, N, H, W, s, launches, nullptr)
                    : pfrb_tc<1>(tw, w, blk, N, H, W, s, launches, nullptr);
   if (rc) return rc;
-  planes_to_f32_kernel<<<148 * 8, 256, 0, s>>>((const __half*)w.actA[0], (const __half*)w.actA[1], n, ns, frames_out);
+  planes_to_f32_kernel<<<148 * 8, 256, 0, s>>>((const __half*)w.actA[0], (const __half*)w.actA[1], n,
+                                               (long long)H * W, ns, frames_out);
   PFNL_LAUNCH_CHECK();
   *launches += 2;
   return PFNL_OK;

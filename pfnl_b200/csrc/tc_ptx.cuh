@@ -59,6 +59,20 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, in
                "r"(c2), "r"(c3)
                : "memory");
 }
+// 5-D variants.
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(m), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -200,6 +214,18 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)(base_offset & 7) << 49;
   d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Un-swizzled ("interleave") K-major operand: core matrices of 8 rows x 16 B stored contiguously
+// (128 B); canonical form ((8,m),(8,2)):((8,SBO),(1,LBO)) in fp16 elements - the two 16-byte k-chunks of
+// a K = 16 step are `lbo_bytes` apart, 8-row groups are `sbo_bytes` apart.  No alignment beyond 16 B.
+__device__ __forceinline__ uint64_t make_sdesc_interleave(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
   return d;
 }
 
