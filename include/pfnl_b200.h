@@ -178,6 +178,28 @@ int pfnl_gather_windows(pfnl_handle* h, const float* frames_dev, int F, int fh, 
  *   in_dev fp32 [n] -> out_dev uint8 [n]. */
 int pfnl_quantize_u8(pfnl_handle* h, const float* in_dev, long long n, unsigned char* out_dev, void* stream);
 
+
+/* ---- evaluation metrics on the luma channel ---- */
+
+/* Mean squared Y difference per frame: utils.py AVG_PSNR:216-246 (to_uint8 -> _rgb2ycbcr[:,:,0] -> crop
+ * sp_border -> mean(diff^2); PSNR = 20*log10(255/sqrt(.)) is left to the host) and, with round_y = 1 and
+ * sp_border = 0, matlab/compute_psnr.m (MATLAB's rgb2ycbcr of a uint8 image returns a rounded uint8 Y).
+ *   a_dev, b_dev [F,H,W,3] fp32 RGB in [vmin,vmax] -> msy_dev [F] double. */
+int pfnl_msy(pfnl_handle* h, const float* a_dev, const float* b_dev, int F, int H, int W, float vmin, float vmax,
+             int sp_border, int round_y, double* msy_dev, void* stream);
+/* Mean SSIM per frame exactly as matlab/SSIM.m computes it for RGB uint8 images with its default
+ * arguments: Y = uint8 rgb2ycbcr, 11x11 Gaussian window (sigma 1.5), 'valid', K = (0.01,0.03), L = 255.
+ *   a_dev, b_dev [F,H,W,3] fp32 RGB in [vmin,vmax] (quantised to uint8 first, as a saved PNG is), H,W >= 11
+ *   -> ssim_dev [F] double. */
+int pfnl_ssim_y(pfnl_handle* h, const float* a_dev, const float* b_dev, int F, int H, int W, float vmin,
+                float vmax, double* ssim_dev, void* stream);
+
+/* ---- host utility ---- */
+
+/* CRC-32C (Castagnoli) of a HOST buffer, continuing from `crc` (0 to start): the checksum of TensorFlow's
+ * tensor-bundle checkpoints (tf.train.Saver, base_model.py:219-243) read by pfnl_b200/tf_checkpoint.py. */
+uint32_t pfnl_crc32c(const void* data_host, size_t n, uint32_t crc);
+
 #ifdef __cplusplus
 }
 #endif

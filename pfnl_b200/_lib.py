@@ -73,6 +73,9 @@ SYMBOLS = {
     "pfnl_downsample4": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP, _VP]),
     "pfnl_gather_windows": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP, _VP]),
     "pfnl_quantize_u8": (_I, [_VP, _VP, C.c_longlong, _VP, _VP]),
+    "pfnl_msy": (_I, [_VP, _VP, _VP, _I, _I, _I, C.c_float, C.c_float, _I, _I, _VP, _VP]),
+    "pfnl_ssim_y": (_I, [_VP, _VP, _VP, _I, _I, _I, C.c_float, C.c_float, _VP, _VP]),
+    "pfnl_crc32c": (C.c_uint32, [_VP, C.c_size_t, C.c_uint32]),
 }
 
 

@@ -100,6 +100,8 @@ struct pfnl_handle {
   size_t ws_cap = 0;
   double* mse_partial = nullptr;
   int mse_cap = 0;
+  double* metric_buf = nullptr;  // [2][F*H*W] luma planes + partial sums of pfnl_msy / pfnl_ssim_y
+  size_t metric_cap = 0;
   // scratch for pfnl_conv2d_nhwc's on-the-fly weight packing
   float* pack_scratch = nullptr;
   size_t pack_cap = 0;
@@ -352,6 +354,7 @@ int pfnl_create(pfnl_handle** out, int device, const pfnl_weights* wts, int prec
   } while (0)
   TRY(init_conv_ffma());
   TRY(init_nonlocal_ffma());
+  TRY(init_metrics());
   TRY(upload(h, wts->nl_g_kernel, kNL * kNL, &h->nl_g_w));
   TRY(upload(h, wts->nl_g_bias, kNL, &h->nl_g_b));
   TRY(upload(h, wts->nl_w_kernel, kNL * kNL, &h->nl_w_w));
@@ -454,6 +457,7 @@ int pfnl_destroy(pfnl_handle* h) {
   for (void* p : h->allocs) cudaFree(p);
   if (h->ws) cudaFree(h->ws);
   if (h->mse_partial) cudaFree(h->mse_partial);
+  if (h->metric_buf) cudaFree(h->metric_buf);
   if (h->pack_scratch) cudaFree(h->pack_scratch);
   if (h->blur_dev) cudaFree(h->blur_dev);
   if (h->pin_in) cudaFreeHost(h->pin_in);
@@ -861,6 +865,100 @@ int pfnl_quantize_u8(pfnl_handle* h, const float* in, long long n, unsigned char
   if (rc) return rc;
   h->launches += 1;
   return PFNL_OK;
+}
+
+
+// luma planes of both inputs + partial sums live in one lazily grown buffer
+static int metric_scratch(pfnl_handle* h, int F, int H, int W, double** ya, double** yb, double** partial) {
+  const size_t npix = (size_t)F * H * W;
+  const size_t need = 2 * npix + metric_partials(F, H, W);
+  if (need > h->metric_cap) {
+    if (h->metric_buf) {
+      PFNL_CUDA(cudaDeviceSynchronize());
+      PFNL_CUDA(cudaFree(h->metric_buf));
+      h->metric_buf = nullptr;
+      h->metric_cap = 0;
+    }
+    PFNL_CUDA(cudaMalloc((void**)&h->metric_buf, need * sizeof(double)));
+    h->metric_cap = need;
+  }
+  *ya = h->metric_buf;
+  *yb = h->metric_buf + npix;
+  *partial = h->metric_buf + 2 * npix;
+  return PFNL_OK;
+}
+
+int pfnl_msy(pfnl_handle* h, const float* a, const float* b, int F, int H, int W, float vmin, float vmax,
+             int sp_border, int round_y, double* out, void* stream) {
+  if (!h || !a || !b || !out) {
+    set_error("pfnl_msy: NULL argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  if (F <= 0 || H <= 0 || W <= 0 || sp_border < 0 || 2 * sp_border >= H || 2 * sp_border >= W || !(vmax > vmin)) {
+    set_error("pfnl_msy: bad shape F=%d H=%d W=%d sp_border=%d (or vmax <= vmin)", F, H, W, sp_border);
+    return PFNL_ERR_BAD_SHAPE;
+  }
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  double *ya, *yb, *partial;
+  int rc = metric_scratch(h, F, H, W, &ya, &yb, &partial);
+  if (rc) return rc;
+  const long long npix = (long long)F * H * W;
+  if ((rc = launch_luma(a, npix, vmin, vmax, round_y, ya, s))) return rc;
+  if ((rc = launch_luma(b, npix, vmin, vmax, round_y, yb, s))) return rc;
+  if ((rc = launch_ysq(ya, yb, F, H, W, sp_border, partial, out, s))) return rc;
+  h->launches += 4;
+  return PFNL_OK;
+}
+
+int pfnl_ssim_y(pfnl_handle* h, const float* a, const float* b, int F, int H, int W, float vmin, float vmax,
+                double* out, void* stream) {
+  if (!h || !a || !b || !out) {
+    set_error("pfnl_ssim_y: NULL argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  if (F <= 0 || H < 11 || W < 11 || !(vmax > vmin)) {  // SSIM.m returns -Inf below 11x11
+    set_error("pfnl_ssim_y: bad shape F=%d H=%d W=%d (needs at least 11x11; or vmax <= vmin)", F, H, W);
+    return PFNL_ERR_BAD_SHAPE;
+  }
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  double *ya, *yb, *partial;
+  int rc = metric_scratch(h, F, H, W, &ya, &yb, &partial);
+  if (rc) return rc;
+  const long long npix = (long long)F * H * W;
+  if ((rc = launch_luma(a, npix, vmin, vmax, 1, ya, s))) return rc;
+  if ((rc = launch_luma(b, npix, vmin, vmax, 1, yb, s))) return rc;
+  if ((rc = launch_ssim(ya, yb, F, H, W, partial, out, s))) return rc;
+  h->launches += 4;
+  return PFNL_OK;
+}
+
+// Table-driven CRC-32C, 8 bytes per step (slicing-by-8); host only.
+uint32_t pfnl_crc32c(const void* data, size_t n, uint32_t crc) {
+  static uint32_t tab[8][256];
+  static bool ready = false;
+  if (!ready) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? 0x82F63B78u : 0u);
+      tab[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) tab[t][i] = (tab[t - 1][i] >> 8) ^ tab[0][tab[t - 1][i] & 0xFFu];
+    ready = true;
+  }
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  uint32_t c = ~crc;
+  while (n >= 8) {
+    const uint32_t lo = c ^ ((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
+    c = tab[7][lo & 0xFFu] ^ tab[6][(lo >> 8) & 0xFFu] ^ tab[5][(lo >> 16) & 0xFFu] ^ tab[4][lo >> 24] ^
+        tab[3][p[4]] ^ tab[2][p[5]] ^ tab[1][p[6]] ^ tab[0][p[7]];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = tab[0][(c ^ *p++) & 0xFFu] ^ (c >> 8);
+  return ~c;
 }
 
 }  // extern "C"

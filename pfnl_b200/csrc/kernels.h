@@ -115,6 +115,15 @@ int launch_gather_windows(const float* frames, int F, long long frame_elems, int
                           cudaStream_t s);
 int launch_quantize_u8(const float* in, long long n, unsigned char* out, cudaStream_t s);
 
+// ---- metrics.cu -------------------------------------------------------------------------
+constexpr int kMetricChunks = 64;
+int init_metrics();
+size_t metric_partials(int F, int H, int W);  // doubles of partial-sum scratch the two metrics need
+int launch_luma(const float* rgb, long long npix, float vmin, float vmax, int round_y, double* y, cudaStream_t s);
+int launch_ysq(const double* ya, const double* yb, int F, int H, int W, int border, double* partial, double* out,
+               cudaStream_t s);
+int launch_ssim(const double* ya, const double* yb, int F, int H, int W, double* partial, double* out, cudaStream_t s);
+
 // ---- mse.cu -----------------------------------------------------------------------------
 constexpr int kMseChunks = 64;
 int launch_mse(const float* sr, const float* hr, int N, long long per_clip, double* partial /*[N*kMseChunks]*/,

@@ -10,6 +10,9 @@ currency: device memory, streams, pinned host memory).
     test_video_truth              pfnl.py:203   same signature
     test_video_lr                 pfnl.py:264   same signature (alias: testvideo, README.md:31)
     testvideos                    pfnl.py:322   same signature
+    eval()                        pfnl.py:94    same loop (eval_dir list, border 8, centre 15 step 32)
+    load / save                   base_model.py:223-243   TF V2 checkpoints read/written without TF
+    AVG_PSNR                      utils.py:216  PFNL.avg_psnr;  matlab/SSIM.m, compute_psnr.m -> PFNL.ssim_y / psnr_y
 """
 from __future__ import annotations
 
@@ -22,7 +25,7 @@ from os.path import join
 import numpy as np
 import torch
 
-from . import _lib, weights as _weights
+from . import _lib, tf_checkpoint as _tfck, weights as _weights
 from ._lib import check, lib
 
 
@@ -216,6 +219,32 @@ class Engine:
         check(lib.pfnl_quantize_u8(self._h, _ptr(x), x.numel(), _ptr(out), _stream_ptr(self.device)))
         return out
 
+    # -- evaluation metrics on the luma channel ------------------------------
+    def msy(self, a, b, vmin=0.0, vmax=1.0, sp_border=8, round_y=False):
+        """Per-frame mean squared Y difference (utils.py AVG_PSNR / matlab/compute_psnr.m):
+        a, b [F,H,W,3] float32 CUDA -> [F] float64 CUDA."""
+        self._chk_in(a, 4)
+        self._chk_in(b, 4)
+        if a.shape != b.shape or a.shape[-1] != 3:
+            raise ValueError("expected two [F,H,W,3] tensors of the same shape")
+        f, hh, ww, _ = a.shape
+        out = torch.empty((f,), dtype=torch.float64, device=self.device)
+        check(lib.pfnl_msy(self._h, _ptr(a), _ptr(b), f, hh, ww, vmin, vmax, sp_border, 1 if round_y else 0,
+                           _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def ssim_y(self, a, b, vmin=0.0, vmax=1.0):
+        """Per-frame mean SSIM of the luma as matlab/SSIM.m computes it: a, b [F,H,W,3] -> [F] float64."""
+        self._chk_in(a, 4)
+        self._chk_in(b, 4)
+        if a.shape != b.shape or a.shape[-1] != 3:
+            raise ValueError("expected two [F,H,W,3] tensors of the same shape")
+        f, hh, ww, _ = a.shape
+        out = torch.empty((f,), dtype=torch.float64, device=self.device)
+        check(lib.pfnl_ssim_y(self._h, _ptr(a), _ptr(b), f, hh, ww, vmin, vmax, _ptr(out),
+                              _stream_ptr(self.device)))
+        return out
+
     def pfrb(self, blk, frames, n, h, w):
         """frames [N*7,H,W,64] -> one Progressive Fusion Residual Block (pfnl.py:66-71)."""
         self._chk_in(frames, 4)
@@ -281,6 +310,8 @@ class PFNL:
         self.eval_basz = 4
         self.save_dir = './checkpoint/pfnl'
         self.log_dir = './pfnl.txt'
+        self.eval_dir = './data/filelist_val.txt'   # model/pfnl.py:30
+        self.global_step = 0                        # restored from the checkpoint when it holds one
         if device is None:
             device = torch.cuda.current_device() if torch.cuda.is_available() else 0
         self.precision = precision
@@ -304,16 +335,44 @@ class PFNL:
         return True
 
     def load(self, checkpoint_dir=None, step=None):
-        """base_model.py:231-243: restore from `save_dir`; returns False (and keeps the
-        initialiser values) when nothing is found.  Reads `<dir>/pfnl.npz`."""
+        """base_model.py:231-243: restore from `save_dir`; returns False (and keeps the initialiser
+        values) when nothing is found.  Reads, in this order, the TensorFlow V2 checkpoint named by
+        `<dir>/checkpoint` (what `tf.train.Saver.restore` reads; parsed without TF by tf_checkpoint.py -
+        optimizer slots and other non-model variables are ignored) or `<dir>/pfnl.npz`."""
         d = checkpoint_dir or self.save_dir
+        print(" [*] Reading SR checkpoints...")
+        prefix = _tfck.latest_checkpoint(d) if os.path.isdir(d) else None
+        if prefix is not None:
+            names = list(_weights.variable_shapes())
+            have = _tfck.list_variables(prefix)
+            tensors = _tfck.read_bundle(prefix, names + (["global_step"] if "global_step" in have else []))
+            if "global_step" in tensors:
+                self.global_step = int(tensors.pop("global_step"))
+            self.load_weights(tensors)
+            print(" [*] Reading checkpoints...{} Success".format(os.path.basename(prefix)))
+            return True
         p = join(d, "pfnl.npz")
         if os.path.exists(p):
-            print(" [*] Reading checkpoint {}".format(p))
             self.load_weights(p)
+            print(" [*] Reading checkpoints...{} Success".format(os.path.basename(p)))
             return True
-        print(" [!] Reading checkpoints... ERROR (no {}); using Xavier-initialised weights".format(p))
+        print(" [*] Reading checkpoints... ERROR")
         return False
+
+    def save(self, checkpoint_dir=None, step=None):
+        """base_model.py:223-229: `<dir>/VSR-<step>.{index,data-00000-of-00001}` + `<dir>/checkpoint`,
+        in TensorFlow's V2 format so that the reference's own `load` can restore it."""
+        d = checkpoint_dir or self.save_dir
+        step = self.global_step if step is None else int(step)
+        os.makedirs(d, exist_ok=True)
+        if self._weights is None:
+            self._weights = _weights.xavier_init()
+        tensors = dict(self._weights)
+        tensors["global_step"] = np.array(step, np.int64)
+        name = "VSR-{}".format(step)
+        _tfck.write_bundle(join(d, name), tensors)
+        _tfck.write_checkpoint_state(d, name)
+        return join(d, name)
 
     @property
     def engine(self):
@@ -345,6 +404,86 @@ class PFNL:
     def psnr(mse):
         """10*log10(1/mse) (pfnl.py:139)."""
         return 10.0 * np.log10(1.0 / np.asarray(mse, dtype=np.float64))
+
+    # -- quality metrics on the luma channel -----------------------------------------------
+    def _dev4(self, v):
+        t = torch.as_tensor(np.asarray(v) if not isinstance(v, torch.Tensor) else v)
+        return t.to(device=self.engine.device, dtype=torch.float32).contiguous()
+
+    def avg_psnr(self, vid_true, vid_pred, vmin=0, vmax=255, t_border=2, sp_border=8):
+        """utils.py:216-246 (AVG_PSNR with RGB inputs): mean over the frames t_border..F-t_border of
+        20*log10(255/rmse) of the luma difference, spatially cropped by sp_border."""
+        m = self.engine.msy(self._dev4(vid_true), self._dev4(vid_pred), float(vmin), float(vmax), sp_border, False)
+        m = m.cpu().numpy()
+        m = m[t_border:m.shape[0] - t_border]
+        return float(np.mean(20 * np.log10(255. / np.sqrt(m))))
+
+    def psnr_y(self, img1, img2):
+        """matlab/compute_psnr.m on uint8-range RGB images [H,W,3] or stacks [F,H,W,3] (values 0..255)."""
+        a, b = self._dev4(img1), self._dev4(img2)
+        if a.dim() == 3:
+            a, b = a[None], b[None]
+        m = self.engine.msy(a, b, 0.0, 255.0, 0, True).cpu().numpy()
+        return 20 * np.log10(255.0 / np.sqrt(m))
+
+    def ssim_y(self, img1, img2):
+        """matlab/SSIM.m (default arguments) on uint8-range RGB images [H,W,3] or stacks [F,H,W,3]."""
+        a, b = self._dev4(img1), self._dev4(img2)
+        if a.dim() == 3:
+            a, b = a[None], b[None]
+        return self.engine.ssim_y(a, b, 0.0, 255.0).cpu().numpy()
+
+    # -- validation loop (model/pfnl.py:94-149) -----------------------------------------------
+    def eval(self, eval_dir=None):
+        """The reference's `eval`: for every sequence listed in `eval_dir`, centre frames 15, 47, ... ->
+        7-frame ground-truth windows cropped to eval_in_size*4 at border 8 -> LR by blur + x4 decimation
+        (DownSample, utils.py:108-134 == DownSample_4D per frame) -> forward -> per-clip MSE -> PSNR; prints
+        and appends the same log line.  Returns (psnr_avg, mse_avg) like the printed values."""
+        print('Evaluating ...')
+        if self._weights is None:
+            self.load(self.save_dir)
+        eng = self.engine
+        border = 8
+        in_h, in_w = self.eval_in_size
+        out_h, out_w = in_h * self.scale, in_w * self.scale
+        filenames = open(eval_dir or self.eval_dir, 'rt').read().splitlines()
+        gt_list = [sorted(glob.glob(join(f, 'truth', '*.png'))) for f in filenames]
+        center = 15
+        batch_gt = []
+        batch_cnt = 0
+        mse_acc = None
+        for gtlist in gt_list:
+            max_frame = len(gtlist)
+            for idx0 in range(center, max_frame, 32):
+                index = np.array([i for i in range(idx0 - self.num_frames // 2, idx0 + self.num_frames // 2 + 1)])
+                index = np.clip(index, 0, max_frame - 1).tolist()
+                gt = [cv2_imread(gtlist[i]) for i in index]
+                gt = [i[border:out_h + border, border:out_w + border, :].astype(np.float32) / 255.0 for i in gt]
+                batch_gt.append(np.stack(gt, axis=0))
+                if len(batch_gt) == self.eval_basz:
+                    gt_dev = torch.as_tensor(np.stack(batch_gt, 0)).to(eng.device).contiguous()   # [B,7,oh,ow,3]
+                    lr = eng.downsample4(gt_dev.view(-1, out_h, out_w, 3)).view(len(batch_gt), self.num_frames,
+                                                                               in_h, in_w, 3)
+                    sr = eng.forward(lr)
+                    mid = self.num_frames // 2
+                    mse_val = eng.mse(sr, gt_dev[:, mid:mid + 1].contiguous())[:, None].cpu().numpy()
+                    mse_acc = mse_val if mse_acc is None else np.concatenate([mse_acc, mse_val], axis=0)
+                    batch_gt = []
+                    print('\tEval batch {} - {} ...'.format(batch_cnt, batch_cnt + self.eval_basz))
+                    batch_cnt += self.eval_basz
+        if mse_acc is None:
+            raise ValueError("eval: fewer than eval_basz={} clips found under {}".format(self.eval_basz,
+                                                                                        eval_dir or self.eval_dir))
+        psnr_acc = 10 * np.log10(1.0 / mse_acc)
+        mse_avg = np.mean(mse_acc, axis=0)
+        psnr_avg = np.mean(psnr_acc, axis=0)
+        print('Eval PSNR: {}, MSE: {}'.format(psnr_avg, mse_avg))
+        with open(self.log_dir, 'a+') as f:
+            mse_log = (mse_avg * 1e6).astype(np.int64) / (1e6)
+            psnr_log = (psnr_avg * 1e6).astype(np.int64) / (1e6)
+            f.write('{' + '"Iter": {} , "PSNR": {}, "MSE": {}'.format(self.global_step, psnr_log.tolist(),
+                                                                     mse_log.tolist()) + '}\n')
+        return psnr_avg, mse_avg
 
     # -- video harnesses (model/pfnl.py:203-332) -------------------------------------------
     def _window_list(self, lrs):
