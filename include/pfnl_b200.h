@@ -51,7 +51,9 @@ typedef enum pfnl_status {
 typedef enum pfnl_precision {
   PFNL_PREC_FP32 = 0,       /* FFMA everywhere: the <=1e-3 parity path */
   PFNL_PREC_TC_FP16X3 = 1,  /* tcgen05 convs on hi/lo-split fp16 operands (3 MMAs, fp32 accumulate) */
-  PFNL_PREC_TC_FP16 = 2     /* tcgen05 convs + tcgen05 non-local block on fp16 operands, fp32 accumulate */
+  PFNL_PREC_TC_FP16 = 2,    /* tcgen05 convs + tcgen05 non-local block on fp16 operands, fp32 accumulate */
+  PFNL_PREC_TC_FP16X3_NLTC = 3 /* convs as FP16X3, non-local block on tcgen05 with fp16 operands (BASELINE configs[1]:
+                                  "fp16 tensor-core non-local"); meets 1e-3 only for trained-like weights */
 } pfnl_precision;
 
 /* Weights, HOST pointers, TF layouts (kernels HWIO [kh,kw,Cin,Cout], biases [Cout]).

@@ -28,7 +28,8 @@ ERR_NO_MEMORY = -6
 PREC_FP32 = 0
 PREC_TC_FP16X3 = 1
 PREC_TC_FP16 = 2
-PRECISIONS = {"fp32": PREC_FP32, "fp16x3": PREC_TC_FP16X3, "fp16": PREC_TC_FP16}
+PREC_TC_FP16X3_NLTC = 3
+PRECISIONS = {"fp32": PREC_FP32, "fp16x3": PREC_TC_FP16X3, "fp16": PREC_TC_FP16, "fp16x3_nltc": PREC_TC_FP16X3_NLTC}
 
 _fp = C.POINTER(C.c_float)
 

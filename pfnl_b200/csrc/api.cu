@@ -259,7 +259,7 @@ int forward_launches(pfnl_handle* h, const float* lr, int N, int H, int W, float
   h->prof.end(s);
   if (rc) return rc;
   h->launches += 1;
-  if (h->precision == PFNL_PREC_TC_FP16 && tc_has_nonlocal()) {
+  if (tc_nl_on_tensor_cores(h->precision) && tc_has_nonlocal()) {
     if ((rc = tc_nonlocal(h->tcw, w.tc, w.tokens, lr, N, H, W, w.inp21, s, &h->launches, &h->prof))) return rc;
   } else {
     h->prof.begin(kProfNonlocal, s);
@@ -332,7 +332,7 @@ int pfnl_create(pfnl_handle** out, int device, const pfnl_weights* wts, int prec
     return PFNL_ERR_BAD_ARG;
   }
   *out = nullptr;
-  if (precision < PFNL_PREC_FP32 || precision > PFNL_PREC_TC_FP16) {
+  if (precision < PFNL_PREC_FP32 || precision > PFNL_PREC_TC_FP16X3_NLTC) {
     set_error("pfnl_create: unknown precision %d", precision);
     return PFNL_ERR_BAD_ARG;
   }
@@ -683,7 +683,7 @@ int pfnl_nonlocal(pfnl_handle* h, const float* tokens, int N, int L, float* out,
   }
   DeviceGuard guard(h->device);
   cudaStream_t s = (cudaStream_t)stream;
-  if (h->precision == PFNL_PREC_TC_FP16 && tc_has_nonlocal()) return tc_nonlocal_tokens(h->tcw, tokens, N, L, out, s, &h->launches);
+  if (tc_nl_on_tensor_cores(h->precision) && tc_has_nonlocal()) return tc_nonlocal_tokens(h->tcw, tokens, N, L, out, s, &h->launches);
   // scratch: G and Y live in the workspace sized for an equivalent (N, 2, 2L) frame
   int rc = ensure_workspace(h, N, 2, 2 * L);
   if (rc) return rc;

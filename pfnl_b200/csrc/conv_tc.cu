@@ -973,7 +973,7 @@ int pack_weights(const float* hwio, int taps, int cin_total, int ci_off, int cou
 }  // namespace
 
 void tc_carve(TcWorkspace& w, int precision, int N, int H, int W, const std::function<char*(size_t)>& take) {
-  const int nsplit = precision == PFNL_PREC_TC_FP16X3 ? 2 : 1;
+  const int nsplit = tc_nsplit(precision);
   for (int pl = 0; pl < 2; ++pl) {
     w.actA[pl] = w.actB[pl] = w.base[pl] = nullptr;
   }
@@ -985,7 +985,7 @@ void tc_carve(TcWorkspace& w, int precision, int N, int H, int W, const std::fun
   w.pbase = (float*)take((size_t)N * H * W * 64 * sizeof(float));
   w.nl_x16 = nullptr;
   w.nl_priv = nullptr;
-  if (precision == PFNL_PREC_TC_FP16 && tc_has_nonlocal()) {
+  if (tc_nl_on_tensor_cores(precision) && tc_has_nonlocal()) {
     const int L = (H / 2) * (W / 2);
     w.nl_x16 = take(tc_nl_workspace_bytes(N, L));
     w.nl_priv = take((size_t)N * L * kNL * sizeof(float));  // Y = softmax(S) * G, fp32 [N,L,84]
@@ -1003,7 +1003,7 @@ int tc_init(TcWeights& tw, int precision, const TcRawWeights& raw, std::vector<v
   PFNL_CUDA(cudaGetDeviceProperties(&prop, dev));
   g_num_sms = prop.multiProcessorCount;
   tw.precision = precision;
-  tw.nsplit = precision == PFNL_PREC_TC_FP16X3 ? 2 : 1;
+  tw.nsplit = tc_nsplit(precision);
   tw.raw = raw;
   int rc;
   if ((rc = set_attr<Shapes<1>::C3, Shapes<1>::C10, 1>())) return rc;
@@ -1170,13 +1170,13 @@ int trunk_tc(const TcWeights& tw, TcWorkspace& w, const float* inp21, int N, int
 
 int tc_trunk(const TcWeights& tw, TcWorkspace& w, int precision, const float* inp21, int N, int H, int W,
              float* merge, cudaStream_t s, long long* launches, Profiler* prof) {
-  if (precision == PFNL_PREC_TC_FP16X3) return trunk_tc<2>(tw, w, inp21, N, H, W, merge, s, launches, prof);
+  if (tc_nsplit(precision) == 2) return trunk_tc<2>(tw, w, inp21, N, H, W, merge, s, launches, prof);
   return trunk_tc<1>(tw, w, inp21, N, H, W, merge, s, launches, prof);
 }
 
 int tc_pfrb_fp32io(const TcWeights& tw, TcWorkspace& w, int precision, int blk, const float* frames, int N, int H,
                    int W, float* frames_out, cudaStream_t s, long long* launches) {
-  const int ns = precision == PFNL_PREC_TC_FP16X3 ? 2 : 1;
+  const int ns = tc_nsplit(precision);
   const long long n = (long long)N * kFrames * H * W * 64;
   f32_to_planes_kernel<<<148 * 8, 256, 0, s>>>(frames, n, (long long)H * W, ns, (__half*)w.actA[0],
                                                (__half*)w.actA[1]);

@@ -15,24 +15,49 @@
 
 namespace pfnl {
 
-// Y[rows,84] = X[rows,84] * Wm[84,84] + b.  CTA = kLinRows rows, 252 active threads:
-// thread -> 4 output columns (21 column groups) x kLinIter rows (12 row groups).
-constexpr int kLinRows = 12;            // rows per CTA: 12 row groups x kLinIter rows (small CTAs: the two
-constexpr int kLinIter = kLinRows / 12;  // 84x84 linears are latency-bound, so spread them over >2 waves)
-
-template <bool SCATTER>
+// Y[rows,84] = X[rows,84] * Wm[84,84] + b.  CTA = 12 * ITER rows, 252 active threads:
+// thread -> 4 output columns (21 column groups) x ITER rows (12 row groups).  Every CTA stages the whole
+// 28 KB weight matrix, so ITER grows with the row count: 1 (12 rows per CTA) keeps the latency-bound
+// small cases (bench: 4096 rows) spread over > 2 waves, 4 (48 rows) amortises the weights for long clips.
+template <bool SCATTER, int ITER>
 __global__ void __launch_bounds__(256) nl_linear_kernel(const float* __restrict__ X, int rows,
                                                         const float* __restrict__ Wm, const float* __restrict__ b,
                                                         float* __restrict__ Y, const float* __restrict__ lr, int H,
                                                         int W) {
   __shared__ __align__(16) float wsm[kNL * kNL];
+  constexpr int kLinRows = 12 * ITER, kLinIter = ITER;
   __shared__ __align__(16) float xsm[kLinRows * kNL];
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * kLinRows;
-  for (int i = tid; i < kNL * kNL; i += 256) wsm[i] = Wm[i];
-  for (int i = tid; i < kLinRows * kNL; i += 256) {
-    int rr = row0 + i / kNL;
-    xsm[i] = rr < rows ? X[(long long)row0 * kNL + i] : 0.f;
+  // staging is the latency of this kernel: 16-byte loads, all issued before the first use
+  {
+    constexpr int NW4 = kNL * kNL / 4;  // 1764 float4
+    const float4* w4 = reinterpret_cast<const float4*>(Wm);
+    float4 wv[(NW4 + 255) / 256];
+#pragma unroll
+    for (int u = 0; u < (NW4 + 255) / 256; ++u) {
+      const int i = tid + u * 256;
+      wv[u] = i < NW4 ? w4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    constexpr int NX4 = kLinRows * kNL / 4;  // a row is 21 float4
+    const float4* x4 = reinterpret_cast<const float4*>(X + (long long)row0 * kNL);
+    float4 xv[(NX4 + 255) / 256];
+#pragma unroll
+    for (int u = 0; u < (NX4 + 255) / 256; ++u) {
+      const int i = tid + u * 256;
+      const bool ok = i < NX4 && row0 + i / (kNL / 4) < rows;
+      xv[u] = ok ? x4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < (NW4 + 255) / 256; ++u) {
+      const int i = tid + u * 256;
+      if (i < NW4) reinterpret_cast<float4*>(wsm)[i] = wv[u];
+    }
+#pragma unroll
+    for (int u = 0; u < (NX4 + 255) / 256; ++u) {
+      const int i = tid + u * 256;
+      if (i < NX4) reinterpret_cast<float4*>(xsm)[i] = xv[u];
+    }
   }
   __syncthreads();
   if (tid >= 252) return;
@@ -83,7 +108,10 @@ __global__ void __launch_bounds__(256) nl_linear_kernel(const float* __restrict_
 
 int launch_nl_linear(const float* X, int rows, const float* Wm, const float* b, float* Y, cudaStream_t s) {
   if (rows <= 0) return PFNL_OK;
-  nl_linear_kernel<false><<<ceil_div(rows, kLinRows), 256, 0, s>>>(X, rows, Wm, b, Y, nullptr, 0, 0);
+  if (rows > 8192)
+    nl_linear_kernel<false, 4><<<ceil_div(rows, 48), 256, 0, s>>>(X, rows, Wm, b, Y, nullptr, 0, 0);
+  else
+    nl_linear_kernel<false, 1><<<ceil_div(rows, 12), 256, 0, s>>>(X, rows, Wm, b, Y, nullptr, 0, 0);
   PFNL_LAUNCH_CHECK();
   return PFNL_OK;
 }
@@ -92,7 +120,10 @@ int launch_nl_linear_scatter(const float* Yin, const float* lr, int N, int H, in
                              const float* bw, float* inp21, cudaStream_t s) {
   const int rows = N * (H / 2) * (W / 2);
   if (rows <= 0) return PFNL_OK;
-  nl_linear_kernel<true><<<ceil_div(rows, kLinRows), 256, 0, s>>>(Yin, rows, Ww, bw, inp21, lr, H, W);
+  if (rows > 8192)
+    nl_linear_kernel<true, 4><<<ceil_div(rows, 48), 256, 0, s>>>(Yin, rows, Ww, bw, inp21, lr, H, W);
+  else
+    nl_linear_kernel<true, 1><<<ceil_div(rows, 12), 256, 0, s>>>(Yin, rows, Ww, bw, inp21, lr, H, W);
   PFNL_LAUNCH_CHECK();
   return PFNL_OK;
 }

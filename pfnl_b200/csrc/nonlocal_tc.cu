@@ -5,13 +5,16 @@
 //                    G = X*Wg+bg (utils.py:26, fp32 FFMA) -> Gt16 [N,96,Lp] fp16 (V, stored
 //                    channel-major so that the PV B-operand is K-major)
 //   nl_tc_kernel     per (clip, 128-query tile): TMA -> smem, S = Q K^T (tcgen05, fp32 in TMEM),
-//                    online softmax (each of 128 threads owns one query row of S: row max / exp /
-//                    sum are thread-local, no shuffles), P (fp16) -> smem, O += P V (tcgen05),
-//                    running-max correction of the TMEM-resident O (tcgen05.ld/st), Y = O / l.
+//                    online softmax on 8 warps (two threads per query row, 64 keys each: row max
+//                    exchanged through smem, exp / sum thread-local), P (fp16) -> smem, O += P V
+//                    (tcgen05), LAZY running-max correction of the TMEM-resident O (tcgen05.ld/st
+//                    only when the row max grows by more than 8: P <= e^8 stays far inside fp16 and
+//                    the common scale cancels in Y = O / l).
 //                    The L x L matrix (utils.py:53-58) is never materialised.
 //   then             Z = Y*Ww+bw, depth_to_space, + input  (nl_linear_scatter, nonlocal_ffma.cu)
 //
-// Shared memory / TMEM per CTA: Q 32 KB, 2 x (K 32 KB + V 24 KB) ring, P 32 KB; TMEM 2 x 128
+// Shared memory / TMEM per CTA: Q 32 KB, 2 x (K 32 KB + V 24 KB) ring, 2 x P 32 KB (softmax(j+1) writes one
+// buffer while the PV product of tile j still reads the other); TMEM 2 x 128
 // columns of S (double buffered: S(j+1) is issued while softmax(j) runs) + 96 columns of O.
 #include <cuda_fp16.h>
 #include <math.h>
@@ -33,12 +36,18 @@ constexpr int kKT = 128;   // keys per tile
 constexpr int kCP = 128;   // padded channel count of X16 (84 -> 128: two 64-wide K blocks)
 constexpr int kVR = 96;    // padded channel count of Gt16 rows (84 -> 96, multiple of 16)
 
+constexpr int kNlSoftmaxWarps = 8;                       // 4 TMEM lane quarters x 2 column halves
+constexpr int kNlThreads = (2 + kNlSoftmaxWarps) * 32;  // + TMA warp + MMA warp = 320
+constexpr float kNlRescaleThreshold = 8.f;
+
 struct NlCtrl {
+  float rowmax[2][2][kQT];  // [tile parity][column half][row]: per-tile row maxima of the two half-row threads
+  float rowsum[2][kQT];     // [column half][row]: final softmax denominators of the two half-row threads
   uint64_t q_full;
   uint64_t k_full[2], k_empty[2];
   uint64_t v_full[2], v_empty[2];
   uint64_t s_full[2], s_empty[2];
-  uint64_t p_ready, pv_done;
+  uint64_t p_ready, pv_done[2];  // pv_done[b]: the PV product reading P buffer b has completed
   uint32_t tmem_base;
 };
 
@@ -46,7 +55,7 @@ constexpr int kQBytes = 2 * kQT * 128;          // 32768
 constexpr int kKBytes = 2 * kKT * 128;          // 32768
 constexpr int kVBytes = 2 * kVR * 128;          // 24576
 constexpr int kPBytes = 2 * kQT * 128;          // 32768
-constexpr int kNlSmem = 1024 + kQBytes + 2 * (kKBytes + kVBytes) + kPBytes + 1024;
+constexpr int kNlSmem = 1024 + kQBytes + 2 * (kKBytes + kVBytes) + 2 * kPBytes + 3072;
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -57,6 +66,14 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
       "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 __device__ __forceinline__ bool elect_one_nl() {
@@ -83,7 +100,7 @@ int make_mat_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kNlThreads, 1)
     nl_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g, int L, int Lp,
                  float* __restrict__ Y) {
   extern __shared__ uint8_t smem_raw[];
@@ -91,8 +108,8 @@ __global__ void __launch_bounds__(192, 1)
   uint8_t* q_sm = smem;
   uint8_t* k_sm = q_sm + kQBytes;            // [2][kKBytes]
   uint8_t* v_sm = k_sm + 2 * kKBytes;        // [2][kVBytes]
-  uint8_t* p_sm = v_sm + 2 * kVBytes;
-  NlCtrl* ctl = reinterpret_cast<NlCtrl*>(p_sm + kPBytes);
+  uint8_t* p_sm = v_sm + 2 * kVBytes;        // [2][kPBytes]
+  NlCtrl* ctl = reinterpret_cast<NlCtrl*>(p_sm + 2 * kPBytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = blockIdx.y, q0 = blockIdx.x * kQT;
   const int ntiles = Lp / kKT;
@@ -105,10 +122,11 @@ __global__ void __launch_bounds__(192, 1)
       mbar_init(&ctl->v_full[i], 1);
       mbar_init(&ctl->v_empty[i], 1);
       mbar_init(&ctl->s_full[i], 1);
-      mbar_init(&ctl->s_empty[i], 4);
+      mbar_init(&ctl->s_empty[i], kNlSoftmaxWarps);
     }
-    mbar_init(&ctl->p_ready, 4);
-    mbar_init(&ctl->pv_done, 1);
+    mbar_init(&ctl->p_ready, kNlSoftmaxWarps);
+    mbar_init(&ctl->pv_done[0], 1);
+    mbar_init(&ctl->pv_done[1], 1);
     fence_mbar_init();
     fence_proxy_async();
     tma_prefetch_desc(&tm_x);
@@ -146,7 +164,6 @@ __global__ void __launch_bounds__(192, 1)
     constexpr uint32_t idesc_s = make_idesc_f16(128, 128);
     constexpr uint32_t idesc_o = make_idesc_f16(128, kVR);
     const uint64_t qd = make_sdesc_sw128(smem_u32(q_sm), 1024, 0);
-    const uint64_t pd = make_sdesc_sw128(smem_u32(p_sm), 1024, 0);
     auto issue_s = [&](int j) {
       const int st = j & 1, ph = (j >> 1) & 1;
       mbar_wait(&ctl->k_full[st], ph);
@@ -174,6 +191,7 @@ __global__ void __launch_bounds__(192, 1)
       mbar_wait(&ctl->p_ready, j & 1);
       fence_after_sync();
       const uint64_t vd = make_sdesc_sw128(smem_u32(v_sm + st * kVBytes), 1024, 0);
+      const uint64_t pd = make_sdesc_sw128(smem_u32(p_sm + st * kPBytes), 1024, 0);
       if (elect_one_nl()) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
@@ -182,31 +200,32 @@ __global__ void __launch_bounds__(192, 1)
           mma_f16(tm_o, pd + aoff, vd + boff, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
         }
         mma_commit(&ctl->v_empty[st]);
-        mma_commit(&ctl->pv_done);
+        mma_commit(&ctl->pv_done[st]);
       }
       __syncwarp();
     }
   } else {
-    // softmax / correction / epilogue: thread <-> query row
-    const int qd = warp & 3;
+    // softmax / correction / epilogue: two threads per query row (column halves of S and of O)
+    const int qd = warp & 3;              // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;     // 0: keys 0..63 / O columns 0..47 ; 1: keys 64..127 / O columns 48..95
     const int row = qd * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;  // m_run: the reference max the exponentials are taken against
     for (int j = 0; j < ntiles; ++j) {
       const int st = j & 1, ph = (j >> 1) & 1;
       mbar_wait(&ctl->s_full[st], ph);
       fence_after_sync();
-      const int kvalid = L - j * kKT;  // keys >= kvalid in this tile are padding
+      const int kvalid = L - j * kKT - half * 64;  // keys >= kvalid of this thread's 64 are padding
       float mt = -INFINITY;
-      uint32_t sreg[4][32];
+      uint32_t sreg[2][32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tm_s0 + st * 128 + lane_addr + c * 32, sreg[c]);
+      for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tm_s0 + st * 128 + lane_addr + half * 64 + c * 32, sreg[c]);
       tmem_ld_wait();
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->s_empty[st]);
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           float s = __uint_as_float(sreg[c][i]);
@@ -214,29 +233,40 @@ __global__ void __launch_bounds__(192, 1)
           sreg[c][i] = __float_as_uint(s);
           mt = fmaxf(mt, s);
         }
-      const float m_new = fmaxf(m_run, mt);   // finite: every tile holds at least one valid key
-      const float alpha = __expf(m_run - m_new);
+      // row max over both halves (the partner thread lives in another warp): smem + named barrier
+      ctl->rowmax[j & 1][half][row] = mt;
+      asm volatile("bar.sync 1, %0;" ::"n"(kNlSoftmaxWarps * 32) : "memory");
+      mt = fmaxf(mt, ctl->rowmax[j & 1][half ^ 1][row]);  // finite: every tile holds at least one valid key
+      // lazy rescaling: keep the old reference while the max grew by at most the threshold
+      const bool bump = mt > m_run + kNlRescaleThreshold;  // identical in both threads of the row
+      const float m_new = bump ? mt : m_run;
+      const float alpha = bump ? __expf(m_run - m_new) : 1.f;  // first tile: exp(-inf) = 0, O and l are empty
       m_run = m_new;
       float psum = 0.f;
-      // previous PV must be complete before P is overwritten and before O is rescaled
-      if (j > 0) {
-        mbar_wait(&ctl->pv_done, (j - 1) & 1);
+      // O may only be rescaled once every PV product issued so far has landed (they complete in order)
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+        mbar_wait(&ctl->pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
         fence_after_sync();
-        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+        // this thread's half of the 96 O columns: 32 + 16
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(tm_o + lane_addr + half * 48, o);
+        tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(tm_o + lane_addr + c * 32, o);
-            tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st_32x32b_x32(tm_o + lane_addr + half * 48, o);
+        uint32_t o2[16];
+        tmem_ld_32x32b_x16(tm_o + lane_addr + half * 48 + 32, o2);
+        tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32b_x32(tm_o + lane_addr + c * 32, o);
-          }
-          tmem_st_wait();
-        }
+        for (int i = 0; i < 16; ++i) o2[i] = __float_as_uint(__uint_as_float(o2[i]) * alpha);
+        tmem_st_32x32b_x16(tm_o + lane_addr + half * 48 + 32, o2);
+        tmem_st_wait();
       }
+      // this tile's P buffer was last read by the PV product of tile j-2
+      if (j >= 2) mbar_wait(&ctl->pv_done[st], ((j - 2) >> 1) & 1);
+      uint8_t* pbuf = p_sm + st * kPBytes;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
           __align__(16) __half hp[8];
@@ -246,9 +276,9 @@ __global__ void __launch_bounds__(192, 1)
             hp[i] = __float2half_rn(pv);
             psum += __half2float(hp[i]);
           }
-          const int chunk = c * 4 + g8;  // 16-byte chunk index along the 128 keys
+          const int chunk = half * 8 + c * 4 + g8;  // 16-byte chunk index along the 128 keys
           const uint32_t off = (chunk >> 3) * (kQT * 128) + sw128_offset(row, chunk & 7);
-          *reinterpret_cast<uint4*>(p_sm + off) = *reinterpret_cast<const uint4*>(hp);
+          *reinterpret_cast<uint4*>(pbuf + off) = *reinterpret_cast<const uint4*>(hp);
         }
       }
       l_run = l_run * alpha + psum;
@@ -257,24 +287,32 @@ __global__ void __launch_bounds__(192, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->p_ready);
     }
-    mbar_wait(&ctl->pv_done, (ntiles - 1) & 1);
+    mbar_wait(&ctl->pv_done[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
     fence_after_sync();
+    // l of the row = sum of the two half-row sums (both were kept against the same reference max)
+    ctl->rowsum[half][row] = l_run;
+    asm volatile("bar.sync 1, %0;" ::"n"(kNlSoftmaxWarps * 32) : "memory");
+    const float inv = 1.f / (l_run + ctl->rowsum[half ^ 1][row]);
     const int q = q0 + row;
-    const float inv = 1.f / l_run;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
+    {
       uint32_t o[32];
-      tmem_ld_32x32b_x32(tm_o + lane_addr + c * 32, o);
+      uint32_t o2[16];
+      tmem_ld_32x32b_x32(tm_o + lane_addr + half * 48, o);
+      tmem_ld_32x32b_x16(tm_o + lane_addr + half * 48 + 32, o2);
       tmem_ld_wait();
       if (q < L) {
-        float* dst = Y + ((long long)n * L + q) * kNL + c * 32;
+        float* dst = Y + ((long long)n * L + q) * kNL + half * 48;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          if (c * 32 + i < kNL)
-            *reinterpret_cast<float4*>(dst + i) =
-                make_float4(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv,
-                            __uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
-        }
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(dst + i) =
+              make_float4(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv,
+                          __uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          if (half * 48 + 32 + i < kNL)
+            *reinterpret_cast<float4*>(dst + 32 + i) =
+                make_float4(__uint_as_float(o2[i]) * inv, __uint_as_float(o2[i + 1]) * inv,
+                            __uint_as_float(o2[i + 2]) * inv, __uint_as_float(o2[i + 3]) * inv);
       }
     }
   }
@@ -336,7 +374,7 @@ static int run_nl_tc(const float* tokens, int N, int L, __half* x16, __half* gt1
     return PFNL_ERR_CUDA;
   }
   dim3 grid(Lp / kQT, N);
-  nl_tc_kernel<<<grid, 192, kNlSmem, s>>>(tmx, tmg, L, Lp, Y);
+  nl_tc_kernel<<<grid, kNlThreads, kNlSmem, s>>>(tmx, tmg, L, Lp, Y);
   PFNL_LAUNCH_CHECK();
   return PFNL_OK;
 }

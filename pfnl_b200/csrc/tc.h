@@ -18,6 +18,14 @@ namespace pfnl {
 constexpr int kTcPatchW3 = 10;
 constexpr int kTcBaseOffsetMode = 0;
 
+// precision mode -> number of fp16 planes of the conv path / whether the non-local block runs on tcgen05
+inline int tc_nsplit(int precision) {
+  return (precision == PFNL_PREC_TC_FP16X3 || precision == PFNL_PREC_TC_FP16X3_NLTC) ? 2 : 1;
+}
+inline bool tc_nl_on_tensor_cores(int precision) {
+  return precision == PFNL_PREC_TC_FP16 || precision == PFNL_PREC_TC_FP16X3_NLTC;
+}
+
 struct TcRawWeights {  // fp32 HWIO device pointers owned by the handle
   const float *nl_g_w, *nl_g_b, *nl_w_w, *nl_w_b;
   const float *nl_gw_w, *nl_gw_b;  // folded output linear of the non-local block: Wg*Ww, bg*Ww+bw

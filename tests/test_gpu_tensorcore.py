@@ -23,7 +23,7 @@ def cu(a):
 def tc_engines(built_lib):
     from pfnl_b200 import Engine
     out = {}
-    for prec in ("fp16x3", "fp16"):
+    for prec in ("fp16x3", "fp16", "fp16x3_nltc"):
         for reg in "AB":
             out[(prec, reg)] = Engine(R.make_weights(reg), device=0, precision=prec, graphs=False)
     return out
@@ -92,6 +92,26 @@ def test_forward_fp16_single_pass_tolerance(tc_engines):
     print(f"fp16 single pass: regime B max-abs {eB:.3e}; regime A max-abs {eA:.3e} (rel {eA / np.abs(refA).max():.3e})")
     assert eB <= 5e-3
     assert eA <= 2e-2 * np.abs(refA).max()
+
+
+def test_forward_fp16x3_with_tensor_core_nonlocal(tc_engines):
+    """BASELINE configs[1] as worded ("fp16 tensor-core non-local") with fp32-grade convs: the fp16-operand
+    non-local block costs ~5e-4 on its O(1) output, so the 1e-3 gate holds for trained-like weights
+    (regime B); with Xavier weights the stack amplifies that error ~100x - reported, bounded relatively."""
+    x = R.make_input(1, 32, 32)
+    yB = tc_engines[("fp16x3_nltc", "B")].forward(cu(x)).cpu().numpy()
+    refB = np.load(os.path.join(GOLD, "forward_B_1x32x32.npz"))["y64"]
+    eB = np.abs(yB - refB).max()
+    yA = tc_engines[("fp16x3_nltc", "A")].forward(cu(x)).cpu().numpy()
+    refA = np.load(os.path.join(GOLD, "forward_A_1x32x32.npz"))["y64"]
+    eA = np.abs(yA - refA).max()
+    print(f"fp16x3 convs + tcgen05 non-local: regime B max-abs {eB:.3e}; regime A max-abs {eA:.3e} "
+          f"(rel {eA / np.abs(refA).max():.3e})")
+    assert eB <= 1e-3
+    assert eA <= 5e-3 * np.abs(refA).max()
+    # the conv stack is bit-identical to plain fp16x3: the two modes differ only through the non-local output
+    y3 = tc_engines[("fp16x3", "B")].forward(cu(x)).cpu().numpy()
+    assert 0 < np.abs(yB - y3).max() <= 2e-3
 
 
 @pytest.mark.parametrize("hh,ww,n", [(16, 16, 2), (8, 8, 3), (10, 6, 2), (13, 10, 1), (32, 32, 1), (64, 64, 1), (1, 1, 1)])
