@@ -16,10 +16,13 @@ currency: device memory, streams, pinned host memory).
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import glob
 import os
+import sys
 import time
+import weakref
 from os.path import join
 
 import numpy as np
@@ -37,6 +40,21 @@ def _stream_ptr(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+_LIVE_ENGINES = weakref.WeakSet()
+
+
+@atexit.register
+def _close_live_engines():
+    """Destroy every handle while the CUDA runtime is still up.  A handle finalised later - during
+    interpreter shutdown, e.g. one kept alive by the traceback of an uncaught exception - would call
+    into a runtime that is being torn down (observed: the process then hangs instead of exiting)."""
+    for e in list(_LIVE_ENGINES):
+        try:
+            e.close()
+        except Exception:
+            pass
+
+
 class Engine:
     """One libpfnl_b200 handle (one device).  Thin, typed wrapper over the C ABI."""
 
@@ -51,6 +69,7 @@ class Engine:
         check(lib.pfnl_create(C.byref(h), self.device.index, C.byref(st), prec))
         del keep
         self._h = h
+        _LIVE_ENGINES.add(self)
         check(lib.pfnl_set_graphs(self._h, 1 if graphs else 0))
 
     def close(self):
@@ -59,6 +78,8 @@ class Engine:
             self._h = None
 
     def __del__(self):
+        if sys.is_finalizing():  # too late for CUDA calls; the atexit hook has already closed live handles
+            return
         try:
             self.close()
         except Exception:
