@@ -130,7 +130,8 @@ struct KernelCfg {
   static_assert(SMEM_BYTES <= SMEM_MAX, "shared memory overflow");
 };
 
-constexpr int kPrefetchAhead = 2;                   // tiles of L2 prefetch distance in the TMA producer
+constexpr int kPrefetchAhead = 0;                   // tiles of L2 prefetch distance in the TMA producer (0 = off: the
+                                                    // prefetches occupy the same TMA engine as the loads they hide)
 constexpr int kTcEpiWarps = 16;                     // 4 TMEM lane quarters x 4 sixteen-channel chunks
 constexpr int kTcThreads = (2 + kTcEpiWarps) * 32;  // + producer warp + MMA warp = 576
 
@@ -239,18 +240,26 @@ __device__ __forceinline__ void load_weights_slice(uint8_t* wsm, const __half* w
 // ---------------------------------------------------------------------------------------------------------
 // role bodies, one call per phase
 // ---------------------------------------------------------------------------------------------------------
+// Issues the patch loads of tiles [first, first + count) of this CTA's tile sequence in phase P (count < 0:
+// all remaining).  The first tile of a phase whose inputs do not depend on the previous phase is issued
+// BEFORE the weight swap (`first = 0, count = 1`), so that its 46 KB do not queue behind the 147 KB image
+// in the TMA engine, which moves only ~40 B/cycle.
 template <class PC, class KC, int NSPLIT>
 __device__ __forceinline__ void producer_phase(const TcPhase& P, const TcCommon& cm, uint8_t* ring, TcCtrl* ctl,
-                                               TcRing& rg, int& tcount) {
+                                               TcRing& rg, int& tcount, int first = 0, int count = -1) {
   constexpr int PAD = (PC::KS - 1) / 2;
+  int seq = 0;
   for (int u = blockIdx.x; u < P.n_units; u += gridDim.x)
-    for (int t = 0; t < P.frames; ++t, ++tcount) {
+    for (int t = 0; t < P.frames; ++t, ++seq) {
+      if (seq < first) continue;
+      if (count >= 0 && seq >= first + count) return;
+      ++tcount;
       const int tx = u % cm.tiles_x;
       const int r = u / cm.tiles_x;
       const int ty = r % cm.tiles_y;
       const int img = (r / cm.tiles_y) * P.frames + t;
       const int x0 = tx * 8 - PAD, y0 = ty * 16 - PAD;
-      {  // L2 prefetch kPrefetchAhead tiles ahead
+      if (kPrefetchAhead > 0) {  // L2 prefetch kPrefetchAhead tiles ahead
         int ft = t + kPrefetchAhead, fu = u;
         while (ft >= P.frames) {
           ft -= P.frames;
@@ -282,7 +291,7 @@ __device__ __forceinline__ void producer_phase(const TcPhase& P, const TcCommon&
           }
         }
       }
-      TC_TRACE(0, 1 + tcount);
+      TC_TRACE(0, tcount);
     }
 }
 
@@ -584,6 +593,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             l2_prefetch_bulk(reinterpret_cast<const uint8_t*>(prog.ph[pi + 1].wimg) + off,
                              (KC::W1 - off) < 16384 ? (KC::W1 - off) : 16384);
         }
+        const bool early = !cm.phase1_reads_phase0;
+        if (early) producer_phase<P1, KC, NSPLIT>(ph, cm, ring, ctl, rg, tcount, 0, 1);
         mbar_wait(&ctl->wfree, (pi - 1) & 1);
         mbar_arrive_expect_tx(&ctl->wfull, KC::W1);
         if (cs > 1) {
@@ -599,7 +610,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           mbar_wait(&ctl->stores_done, (pi - 1) & 1);
           fence_proxy_async_all();
         }
-        producer_phase<P1, KC, NSPLIT>(ph, cm, ring, ctl, rg, tcount);
+        producer_phase<P1, KC, NSPLIT>(ph, cm, ring, ctl, rg, tcount, early ? 1 : 0, -1);
       }
     }
   } else if (warp == 1) {
