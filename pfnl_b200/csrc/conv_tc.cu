@@ -801,6 +801,179 @@ __global__ void __launch_bounds__(256, 2) conv0_planes_kernel(const float* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// conv0 (5x5, 3->64, leaky_relu; model/pfnl.py:48,61-62) on tcgen05: an explicit im2col tile.  K = 75 taps
+// (dy,dx,c) padded to 80 = 5 k-steps; one CTA (128 threads = 128 tile pixels = 128 TMEM lanes) per 16x8
+// tile: stage the 20x12x3 fp32 patch, let every thread write its pixel's 80 operand values as hi/lo fp16
+// core-matrix rows (un-swizzled K-major: [k-chunk][row][8 k]), 5 x (N=128 + N=64) MMAs, epilogue as the
+// other convs.  ~65 KB of smem and 128 TMEM columns per CTA: three CTAs share an SM and overlap each
+// other's phases, which replaces an intra-CTA pipeline.
+template <int NSPLIT>
+struct Conv0Cfg {
+  static constexpr int KC = 10;                       // k-chunks of 8
+  static constexpr int A_BYTES = KC * 128 * 16;       // one plane of the im2col tile
+  static constexpr int B_ROWS = NSPLIT * 64;
+  static constexpr int B_BYTES = KC * B_ROWS * 16;
+  static constexpr int PATCH_FLOATS = 20 * 12 * 3;
+  static constexpr int SMEM = 1024 + NSPLIT * A_BYTES + B_BYTES + PATCH_FLOATS * 4 + 64 * 4 + 64;
+};
+
+// HWIO fp32 [75][64] -> [kc][plane*64 + co][8 k] fp16 (k = (dy*5+dx)*3 + c, zero for k >= 75)
+__global__ void pack_conv0_tc_kernel(const float* __restrict__ hwio, int nsplit, __half* __restrict__ out) {
+  const int rows = nsplit * 64;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 10 * 64 * 8; e += gridDim.x * blockDim.x) {
+    const int kk = e & 7, co = (e >> 3) & 63, kc = e >> 9;
+    const int k = kc * 8 + kk;
+    const float w = k < 75 ? hwio[k * 64 + co] : 0.f;
+    const __half hi = __float2half_rn(w);
+    out[((size_t)kc * rows + co) * 8 + kk] = hi;
+    if (nsplit == 2) out[((size_t)kc * rows + 64 + co) * 8 + kk] = __float2half_rn((w - __half2float(hi)) * 2048.f);
+  }
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(128) conv0_tc_kernel(const float* __restrict__ inp21, int H, int W, int tiles_x,
+                                                       int tiles_y, const __half* __restrict__ wimg,
+                                                       const float* __restrict__ bias, __half* __restrict__ out_hi,
+                                                       __half* __restrict__ out_lo) {
+  using CF = Conv0Cfg<NSPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_sm = smem;                                  // [NSPLIT][KC][128 rows][16 B]
+  uint8_t* b_sm = a_sm + NSPLIT * CF::A_BYTES;           // [KC][B_ROWS][16 B]
+  float* patch = reinterpret_cast<float*>(b_sm + CF::B_BYTES);  // [20][12][3]
+  float* bias_sm = patch + CF::PATCH_FLOATS;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(bias_sm + 64);   // [0]: weights landed, [1]: MMAs done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tile = blockIdx.x;
+  const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, img = tile / (tiles_x * tiles_y);
+  const int n = img / kFrames, t = img % kFrames;
+  const int y0 = ty * 16, x0 = tx * 8;
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+    fence_proxy_async();
+    mbar_arrive_expect_tx(&bar[0], CF::B_BYTES);
+    bulk_load(b_sm, wimg, CF::B_BYTES, &bar[0]);
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 128);
+    tmem_relinquish();
+  }
+  if (tid < 64) bias_sm[tid] = bias[tid];
+  pdl_wait();  // inp21 is written by the previous kernel
+  {  // all loads in flight before the first store: the patch is the latency of this kernel
+    constexpr int NL = (CF::PATCH_FLOATS + 127) / 128;
+    float pv[NL];
+#pragma unroll
+    for (int u = 0; u < NL; ++u) {
+      const int i = tid + u * 128;
+      const int c = i % 3, pp = i / 3;
+      const int py = pp / 12, px = pp % 12;
+      const int gy = y0 + py - 2, gx = x0 + px - 2;
+      pv[u] = 0.f;
+      if (i < CF::PATCH_FLOATS && gy >= 0 && gy < H && gx >= 0 && gx < W)
+        pv[u] = inp21[(((long long)n * H + gy) * W + gx) * 21 + t * 3 + c];
+    }
+#pragma unroll
+    for (int u = 0; u < NL; ++u) {
+      const int i = tid + u * 128;
+      if (i < CF::PATCH_FLOATS) patch[i] = pv[u];
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  // ---- im2col: this thread's pixel = tile row m; its 80 operand values, 8 per 16-byte core-matrix row
+  const int m = tid, my = m >> 3, mx = m & 7;
+#pragma unroll
+  for (int kc = 0; kc < CF::KC; ++kc) {
+    __align__(16) __half hh[8];
+    __align__(16) __half hl[8];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int k = kc * 8 + kk;
+      float v = 0.f;
+      if (k < 75) {
+        const int tap = k / 3, c = k - tap * 3;
+        const int dy = tap / 5, dx = tap - dy * 5;
+        v = patch[((my + dy) * 12 + mx + dx) * 3 + c];
+      }
+      if (NSPLIT == 2)
+        split_half(v, hh[kk], hl[kk]);
+      else
+        hh[kk] = __float2half_rn(v);
+    }
+    *reinterpret_cast<uint4*>(a_sm + (kc * 128 + m) * 16) = *reinterpret_cast<const uint4*>(hh);
+    if (NSPLIT == 2)
+      *reinterpret_cast<uint4*>(a_sm + CF::A_BYTES + (kc * 128 + m) * 16) = *reinterpret_cast<const uint4*>(hl);
+  }
+  fence_proxy_async();  // generic-proxy operand writes -> visible to the tensor core (async proxy)
+  __syncthreads();
+  if (warp == 0) {
+    mbar_wait(&bar[0], 0);
+    fence_after_sync();
+    if (elect_one()) {
+      constexpr uint32_t idesc_hi = make_idesc_f16(128, NSPLIT * 64);
+      constexpr uint32_t idesc_lo = make_idesc_f16(128, 64);
+      // K-major, no swizzle: 8-row groups 128 B apart (SBO), the two k-chunks of a K=16 step LBO apart
+      const uint64_t ad = make_sdesc_interleave(smem_u32(a_sm), 128 * 16, 128);
+      const uint64_t bd = make_sdesc_interleave(smem_u32(b_sm), CF::B_ROWS * 16, 128);
+#pragma unroll
+      for (int ks = 0; ks < 5; ++ks)
+        mma_f16(tmem, ad + ((ks * 2 * 128 * 16) >> 4), bd + ((ks * 2 * CF::B_ROWS * 16) >> 4), idesc_hi, ks > 0);
+      if (NSPLIT == 2) {
+        const uint64_t al = make_sdesc_interleave(smem_u32(a_sm + CF::A_BYTES), 128 * 16, 128);
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks)
+          mma_f16(tmem + 64, al + ((ks * 2 * 128 * 16) >> 4), bd + ((ks * 2 * CF::B_ROWS * 16) >> 4), idesc_lo, 1u);
+      }
+      mma_commit(&bar[1]);
+    }
+    __syncwarp();
+  }
+  pdl_launch_dependents();
+  mbar_wait(&bar[1], 0);
+  fence_after_sync();
+  // ---- epilogue: thread = pixel (TMEM lane), 4 passes of 16 channels
+  const int y = y0 + my, x = x0 + mx;
+  const bool inb = y < H && x < W;
+  const long long cs = (long long)H * W * 8;
+  const uint32_t t0 = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    uint32_t d0[16], d1[16];
+    tmem_ld_32x32b_x16(t0 + c0, d0);
+    if (NSPLIT == 2) tmem_ld_32x32b_x16(t0 + 64 + c0, d1);
+    tmem_ld_wait();
+    U256 oh, ol;
+    __half* ph = reinterpret_cast<__half*>(&oh);
+    __half* pl = reinterpret_cast<__half*>(&ol);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float v = __uint_as_float(d0[j]);
+      if (NSPLIT == 2) v = fmaf(__uint_as_float(d1[j]), 1.f / 2048.f, v);
+      v = lrelu(v + bias_sm[c0 + j]);
+      if (NSPLIT == 2)
+        split_half(v, ph[j], pl[j]);
+      else
+        ph[j] = __float2half_rn(v);
+    }
+    if (inb) {
+      const long long poff = plane_off(img, c0 >> 3, y, x, H, W);
+      st_plane16(out_hi + poff, cs, oh);
+      if (NSPLIT == 2) st_plane16(out_lo + poff, cs, ol);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
 // ---- host side --------------------------------------------------------------------------------------------
 namespace {
 
@@ -1024,7 +1197,17 @@ int tc_init(TcWeights& tw, int precision, const TcRawWeights& raw, std::vector<v
   if ((rc = set_attr<Shapes<2>::C3, Shapes<2>::C3, 2>())) return rc;
   if ((rc = set_attr<Shapes<2>::CM, Shapes<2>::CM, 2>())) return rc;
   if ((rc = tc_nl_init())) return rc;
+  PFNL_CUDA(cudaFuncSetAttribute(conv0_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv0Cfg<1>::SMEM));
+  PFNL_CUDA(cudaFuncSetAttribute(conv0_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv0Cfg<2>::SMEM));
   const int ns = tw.nsplit;
+  {
+    void* d = nullptr;
+    PFNL_CUDA(cudaMalloc(&d, (size_t)10 * ns * 64 * 16));
+    allocs.push_back(d);
+    tw.conv0 = d;
+    pack_conv0_tc_kernel<<<20, 256>>>(raw.conv0_w, ns, (__half*)d);
+    PFNL_LAUNCH_CHECK();
+  }
   for (int i = 0; i < PFNL_NUM_BLOCK; ++i) {
     if ((rc = pack_weights(raw.conv1_w[i], 9, 64, 0, 64, 64, ns, &tw.conv1[i], allocs))) return rc;
     // conv10 [1,1,448,64]: "tap" t = frame slice t (input channels t*64..t*64+63)
@@ -1141,10 +1324,32 @@ int trunk_tc(const TcWeights& tw, TcWorkspace& w, const float* inp21, int N, int
              cudaStream_t s, long long* launches, Profiler* prof) {
   using SH = Shapes<NSPLIT>;
   int rc;
-  dim3 grid(ceil_div(W, 16) * ceil_div(H, 16), N * kFrames);
   if (prof) prof->begin(kProfConv0, s);
-  conv0_planes_kernel<NSPLIT><<<grid, 256, 0, s>>>(inp21, H, W, tw.raw.conv0_w, tw.raw.conv0_b, (__half*)w.actA[0],
-                                                   (__half*)w.actA[1]);
+  static const bool conv0_ffma = getenv("PFNL_TC_CONV0_FFMA") != nullptr;  // the CUDA-core version, kept for A/B runs
+  if (conv0_ffma) {
+    dim3 grid(ceil_div(W, 16) * ceil_div(H, 16), N * kFrames);
+    conv0_planes_kernel<NSPLIT><<<grid, 256, 0, s>>>(inp21, H, W, tw.raw.conv0_w, tw.raw.conv0_b, (__half*)w.actA[0],
+                                                     (__half*)w.actA[1]);
+  } else {
+    const int tiles_x = ceil_div(W, 8), tiles_y = ceil_div(H, 16);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(tiles_x * tiles_y * N * kFrames);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = Conv0Cfg<NSPLIT>::SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    int na = 0;
+    if (pdl_enabled()) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    PFNL_CUDA(cudaLaunchKernelEx(&cfg, conv0_tc_kernel<NSPLIT>, inp21, H, W, tiles_x, tiles_y,
+                                 (const __half*)tw.conv0, tw.raw.conv0_b, (__half*)w.actA[0], (__half*)w.actA[1]));
+  }
   if (prof) prof->end(s);
   PFNL_LAUNCH_CHECK();
   *launches += 1;

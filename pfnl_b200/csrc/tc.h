@@ -54,6 +54,7 @@ struct TcWeights {
   void* conv2b[PFNL_NUM_BLOCK] = {};
   void* conv2f[PFNL_NUM_BLOCK] = {};
   void* merge1 = nullptr;
+  void* conv0 = nullptr;  // [10 k-chunks][nsplit*64 rows][8 k] fp16, un-swizzled core matrices (conv0_tc_kernel)
   float* zero_bias = nullptr;  // [64] zeros
   // non-local (precision 2): fp16 Wg^T image etc.
   void* nl_priv = nullptr;
