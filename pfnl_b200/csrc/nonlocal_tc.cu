@@ -1,9 +1,10 @@
-// Non-local block on tcgen05 tensor cores (PFNL_PREC_TC_FP16): NonLocalBlock nltype=1 'gaussian',
-// sub_sample=1 (utils.py:18-71) with theta = phi = X (utils.py:33-34,41-42).
+// Non-local block on tcgen05 tensor cores: NonLocalBlock nltype=1 'gaussian', sub_sample=1 (utils.py:18-71)
+// with theta = phi = X (utils.py:33-34,41-42).  Two operand precisions (NlCfg<NSPLIT>): fp16 (PFNL_PREC_TC_FP16,
+// _FP16X3_NLTC) and hi/lo-split fp16 pairs = fp32-grade logits and values (PFNL_PREC_TC_FP16X3).
 //
-//   nl_prep_kernel   X fp32 [N,L,84] -> X16 [N,Lp,128] fp16 (zero padded; the Q/K operand) and
-//                    G = X*Wg+bg (utils.py:26, fp32 FFMA) -> Gt16 [N,96,Lp] fp16 (V, stored
-//                    channel-major so that the PV B-operand is K-major)
+//   nl_prep_kernel   X fp32 [N,L,84] -> X16 [N,Lp,128] fp16 (zero padded; the Q/K operand) and X^T -> Xt16
+//                    [N,96,Lp] fp16 (V, stored channel-major so that the PV B-operand is K-major; V = X because
+//                    the g linear is folded into the output linear), each as hi [, lo] planes
 //   nl_tc_kernel     per (clip, 128-query tile): TMA -> smem, S = Q K^T (tcgen05, fp32 in TMEM),
 //                    online softmax on 8 warps (two threads per query row, 64 keys each: row max
 //                    exchanged through smem, exp / sum thread-local), P (fp16) -> smem, O += P V
@@ -11,11 +12,11 @@
 //                    only when the row max grows by more than 8: P <= e^8 stays far inside fp16 and
 //                    the common scale cancels in Y = O / l).
 //                    The L x L matrix (utils.py:53-58) is never materialised.
-//   then             Z = Y*Ww+bw, depth_to_space, + input  (nl_linear_scatter, nonlocal_ffma.cu)
+//   then             Z = Y*(Wg*Ww)+(bg*Ww+bw), depth_to_space, + input  (nl_linear_scatter, nonlocal_ffma.cu)
 //
-// Shared memory / TMEM per CTA: Q 32 KB, 2 x (K 32 KB + V 24 KB) ring, 2 x P 32 KB (softmax(j+1) writes one
-// buffer while the PV product of tile j still reads the other); TMEM 2 x 128
-// columns of S (double buffered: S(j+1) is issued while softmax(j) runs) + 96 columns of O.
+// fp16 mode, per CTA: Q 32 KB, 2 x (K 32 KB + V 24 KB) ring, 2 x P 32 KB (softmax(j+1) writes one buffer while
+// the PV product of tile j still reads the other); TMEM 2 x 128 columns of S (S(j+1) is issued while
+// softmax(j) runs) + 96 columns of O.  Split mode: see NlCfg.
 #include <cuda_fp16.h>
 #include <math.h>
 
@@ -40,6 +41,33 @@ constexpr int kNlSoftmaxWarps = 8;                       // 4 TMEM lane quarters
 constexpr int kNlThreads = (2 + kNlSoftmaxWarps) * 32;  // + TMA warp + MMA warp = 320
 constexpr float kNlRescaleThreshold = 8.f;
 
+// NSPLIT = 1: fp16 operands.  NSPLIT = 2: hi/lo-split operands (x = hi + lo/2048, like the convs):
+//   [S_hh | S_x] = Q_hi x [K_hi ; K_lo]^T (one N = 256 MMA per k-step),  S_x += Q_lo x K_hi^T,  S = S_hh + S_x/2048
+//   [O_h | O_l]  = P x [V_hi ; V_lo]                                       O = O_h + O_l/2048
+// i.e. fp32-grade logits and values; only P (in [0, e^8], normalised by the sum of the SAME rounded values)
+// stays a single fp16.  The split mode has no room to double-buffer (shared memory: Q 64 + K 64 + V 48 +
+// P 32 KB; TMEM: S 256 + O 192 columns), so its stages are single-buffered.
+template <int NSPLIT>
+struct NlCfg {
+  static constexpr int KSTAGES = NSPLIT == 1 ? 2 : 1;  // K/V ring depth
+  static constexpr int SBUFS = NSPLIT == 1 ? 2 : 1;    // S accumulators in TMEM
+  static constexpr int PBUFS = NSPLIT == 1 ? 2 : 1;    // P tiles in shared memory
+  static constexpr int PLANE = kQT * 128;              // one plane of one 64-wide block: 128 rows x 128 B
+  static constexpr int BLK_QK = NSPLIT * PLANE;        // one 64-channel block of Q or K: [hi ; lo] rows
+  static constexpr int Q_BYTES = 2 * BLK_QK;
+  static constexpr int K_BYTES = 2 * BLK_QK;
+  static constexpr int VPLANE = kVR * 128;             // one plane of one 64-key block of V^T: 96 rows x 128 B
+  static constexpr int BLK_V = NSPLIT * VPLANE;
+  static constexpr int V_BYTES = 2 * BLK_V;
+  static constexpr int P_BYTES = 2 * kQT * 128;
+  static constexpr int SMEM = 1024 + Q_BYTES + KSTAGES * (K_BYTES + V_BYTES) + PBUFS * P_BYTES + 3072;
+  static constexpr int S_COLS = NSPLIT * 128;
+  static constexpr int O_COLS = NSPLIT * kVR;
+  static constexpr int TM_O = SBUFS * S_COLS;          // 256 in both modes
+  static_assert(TM_O + O_COLS <= 512, "TMEM overflow");
+  static_assert(SMEM <= 227 * 1024, "shared memory overflow");
+};
+
 struct NlCtrl {
   float rowmax[2][2][kQT];  // [tile parity][column half][row]: per-tile row maxima of the two half-row threads
   float rowsum[2][kQT];     // [column half][row]: final softmax denominators of the two half-row threads
@@ -50,12 +78,6 @@ struct NlCtrl {
   uint64_t p_ready, pv_done[2];  // pv_done[b]: the PV product reading P buffer b has completed
   uint32_t tmem_base;
 };
-
-constexpr int kQBytes = 2 * kQT * 128;          // 32768
-constexpr int kKBytes = 2 * kKT * 128;          // 32768
-constexpr int kVBytes = 2 * kVR * 128;          // 24576
-constexpr int kPBytes = 2 * kQT * 128;          // 32768
-constexpr int kNlSmem = 1024 + kQBytes + 2 * (kKBytes + kVBytes) + 2 * kPBytes + 3072;
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -100,16 +122,37 @@ int make_mat_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
+// this thread's 16/32 columns of O at `col`: multiply by alpha in place
+__device__ __forceinline__ void rescale_o32(uint32_t taddr, float alpha) {
+  uint32_t o[32];
+  tmem_ld_32x32b_x32(taddr, o);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+  tmem_st_32x32b_x32(taddr, o);
+}
+__device__ __forceinline__ void rescale_o16(uint32_t taddr, float alpha) {
+  uint32_t o[16];
+  tmem_ld_32x32b_x16(taddr, o);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+  tmem_st_32x32b_x16(taddr, o);
+}
+
+template <int NSPLIT>
 __global__ void __launch_bounds__(kNlThreads, 1)
-    nl_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g, int L, int Lp,
+    nl_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_xl,
+                 const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_gl, int L, int Lp,
                  float* __restrict__ Y) {
+  using CF = NlCfg<NSPLIT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* q_sm = smem;
-  uint8_t* k_sm = q_sm + kQBytes;            // [2][kKBytes]
-  uint8_t* v_sm = k_sm + 2 * kKBytes;        // [2][kVBytes]
-  uint8_t* p_sm = v_sm + 2 * kVBytes;        // [2][kPBytes]
-  NlCtrl* ctl = reinterpret_cast<NlCtrl*>(p_sm + 2 * kPBytes);
+  uint8_t* q_sm = smem;                                  // [2 blocks][NSPLIT planes][128 rows][128 B]
+  uint8_t* k_sm = q_sm + CF::Q_BYTES;                    // [KSTAGES] x same
+  uint8_t* v_sm = k_sm + CF::KSTAGES * CF::K_BYTES;      // [KSTAGES][2 key blocks][NSPLIT planes][96 rows][128 B]
+  uint8_t* p_sm = v_sm + CF::KSTAGES * CF::V_BYTES;      // [PBUFS][2 key blocks][128 rows][128 B]
+  NlCtrl* ctl = reinterpret_cast<NlCtrl*>(p_sm + CF::PBUFS * CF::P_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = blockIdx.y, q0 = blockIdx.x * kQT;
   const int ntiles = Lp / kKT;
@@ -123,14 +166,17 @@ __global__ void __launch_bounds__(kNlThreads, 1)
       mbar_init(&ctl->v_empty[i], 1);
       mbar_init(&ctl->s_full[i], 1);
       mbar_init(&ctl->s_empty[i], kNlSoftmaxWarps);
+      mbar_init(&ctl->pv_done[i], 1);
     }
     mbar_init(&ctl->p_ready, kNlSoftmaxWarps);
-    mbar_init(&ctl->pv_done[0], 1);
-    mbar_init(&ctl->pv_done[1], 1);
     fence_mbar_init();
     fence_proxy_async();
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_g);
+    if (NSPLIT == 2) {
+      tma_prefetch_desc(&tm_xl);
+      tma_prefetch_desc(&tm_gl);
+    }
   }
   if (warp == 1) {
     tmem_alloc(&ctl->tmem_base, 512);
@@ -140,69 +186,91 @@ __global__ void __launch_bounds__(kNlThreads, 1)
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = ctl->tmem_base;
-  const uint32_t tm_s0 = tmem, tm_o = tmem + 256;
+  const uint32_t tm_s0 = tmem, tm_o = tmem + CF::TM_O;
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(&ctl->q_full, kQBytes);
-      tma_load_2d(q_sm, &tm_x, &ctl->q_full, 0, n * Lp + q0);
-      tma_load_2d(q_sm + kQT * 128, &tm_x, &ctl->q_full, 64, n * Lp + q0);
+      mbar_arrive_expect_tx(&ctl->q_full, CF::Q_BYTES);
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int pl = 0; pl < NSPLIT; ++pl)
+          tma_load_2d(q_sm + b * CF::BLK_QK + pl * CF::PLANE, pl ? &tm_xl : &tm_x, &ctl->q_full, b * 64, n * Lp + q0);
       for (int j = 0; j < ntiles; ++j) {
-        const int st = j & 1, ph = (j >> 1) & 1;
+        const int st = j % CF::KSTAGES, ph = (j / CF::KSTAGES) & 1;
         mbar_wait(&ctl->k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&ctl->k_full[st], kKBytes);
-        tma_load_2d(k_sm + st * kKBytes, &tm_x, &ctl->k_full[st], 0, n * Lp + j * kKT);
-        tma_load_2d(k_sm + st * kKBytes + kKT * 128, &tm_x, &ctl->k_full[st], 64, n * Lp + j * kKT);
+        mbar_arrive_expect_tx(&ctl->k_full[st], CF::K_BYTES);
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int pl = 0; pl < NSPLIT; ++pl)
+            tma_load_2d(k_sm + st * CF::K_BYTES + b * CF::BLK_QK + pl * CF::PLANE, pl ? &tm_xl : &tm_x,
+                        &ctl->k_full[st], b * 64, n * Lp + j * kKT);
         mbar_wait(&ctl->v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&ctl->v_full[st], kVBytes);
-        tma_load_2d(v_sm + st * kVBytes, &tm_g, &ctl->v_full[st], j * kKT, n * kVR);
-        tma_load_2d(v_sm + st * kVBytes + kVR * 128, &tm_g, &ctl->v_full[st], j * kKT + 64, n * kVR);
+        mbar_arrive_expect_tx(&ctl->v_full[st], CF::V_BYTES);
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int pl = 0; pl < NSPLIT; ++pl)
+            tma_load_2d(v_sm + st * CF::V_BYTES + b * CF::BLK_V + pl * CF::VPLANE, pl ? &tm_gl : &tm_g,
+                        &ctl->v_full[st], j * kKT + b * 64, n * kVR);
       }
     }
   } else if (warp == 1) {
     // converged warp, one elected lane issues (see conv_tc.cu); descriptors advance by constant adds
-    constexpr uint32_t idesc_s = make_idesc_f16(128, 128);
-    constexpr uint32_t idesc_o = make_idesc_f16(128, kVR);
+    constexpr uint32_t idesc_s = make_idesc_f16(128, NSPLIT * 128);  // Q_hi x [K_hi ; K_lo]
+    constexpr uint32_t idesc_sx = make_idesc_f16(128, 128);          // Q_lo x K_hi
+    constexpr uint32_t idesc_o = make_idesc_f16(128, NSPLIT * kVR);  // P x [V_hi ; V_lo]
     const uint64_t qd = make_sdesc_sw128(smem_u32(q_sm), 1024, 0);
     auto issue_s = [&](int j) {
-      const int st = j & 1, ph = (j >> 1) & 1;
+      const int st = j % CF::KSTAGES, ph = (j / CF::KSTAGES) & 1;
+      const int sb = j % CF::SBUFS, sph = (j / CF::SBUFS) & 1;
       mbar_wait(&ctl->k_full[st], ph);
-      mbar_wait(&ctl->s_empty[st], ph ^ 1);
+      mbar_wait(&ctl->s_empty[sb], sph ^ 1);
       fence_after_sync();
-      const uint64_t kd = make_sdesc_sw128(smem_u32(k_sm + st * kKBytes), 1024, 0);
+      const uint64_t kd = make_sdesc_sw128(smem_u32(k_sm + st * CF::K_BYTES), 1024, 0);
       if (elect_one_nl()) {
         // channels 0..63 (block 0, 4 k-steps) and 64..95 (block 1, 2 k-steps; 96..127 are zero padding)
 #pragma unroll
         for (int ks = 0; ks < 6; ++ks) {
-          const uint32_t off = ((ks < 4) ? ks * 32 : (kQT * 128 + (ks - 4) * 32)) >> 4;
-          mma_f16(tm_s0 + st * 128, qd + off, kd + off, idesc_s, ks > 0 ? 1u : 0u);
+          const uint32_t off = ((ks >> 2) * CF::BLK_QK + (ks & 3) * 32) >> 4;
+          mma_f16(tm_s0 + sb * CF::S_COLS, qd + off, kd + off, idesc_s, ks > 0 ? 1u : 0u);
+        }
+        if (NSPLIT == 2) {
+#pragma unroll
+          for (int ks = 0; ks < 6; ++ks) {
+            const uint32_t off = ((ks >> 2) * CF::BLK_QK + (ks & 3) * 32) >> 4;
+            mma_f16(tm_s0 + sb * CF::S_COLS + 128, qd + (CF::PLANE >> 4) + off, kd + off, idesc_sx, 1u);
+          }
         }
         mma_commit(&ctl->k_empty[st]);
-        mma_commit(&ctl->s_full[st]);
+        mma_commit(&ctl->s_full[sb]);
       }
       __syncwarp();
     };
     mbar_wait(&ctl->q_full, 0);
     issue_s(0);
     for (int j = 0; j < ntiles; ++j) {
-      if (j + 1 < ntiles) issue_s(j + 1);
-      const int st = j & 1, ph = (j >> 1) & 1;
+      if (CF::SBUFS == 2 && j + 1 < ntiles) issue_s(j + 1);
+      const int st = j % CF::KSTAGES, ph = (j / CF::KSTAGES) & 1;
+      const int pb = j % CF::PBUFS;
       mbar_wait(&ctl->v_full[st], ph);
       mbar_wait(&ctl->p_ready, j & 1);
       fence_after_sync();
-      const uint64_t vd = make_sdesc_sw128(smem_u32(v_sm + st * kVBytes), 1024, 0);
-      const uint64_t pd = make_sdesc_sw128(smem_u32(p_sm + st * kPBytes), 1024, 0);
+      const uint64_t vd = make_sdesc_sw128(smem_u32(v_sm + st * CF::V_BYTES), 1024, 0);
+      const uint64_t pd = make_sdesc_sw128(smem_u32(p_sm + pb * CF::P_BYTES), 1024, 0);
       if (elect_one_nl()) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
           const uint32_t aoff = ((ks >> 2) * (kQT * 128) + (ks & 3) * 32) >> 4;
-          const uint32_t boff = ((ks >> 2) * (kVR * 128) + (ks & 3) * 32) >> 4;
+          const uint32_t boff = ((ks >> 2) * CF::BLK_V + (ks & 3) * 32) >> 4;
           mma_f16(tm_o, pd + aoff, vd + boff, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
         }
         mma_commit(&ctl->v_empty[st]);
-        mma_commit(&ctl->pv_done[st]);
+        mma_commit(&ctl->pv_done[pb]);
       }
       __syncwarp();
+      if (CF::SBUFS == 1 && j + 1 < ntiles) issue_s(j + 1);
     }
   } else {
     // softmax / correction / epilogue: two threads per query row (column halves of S and of O)
@@ -212,26 +280,38 @@ __global__ void __launch_bounds__(kNlThreads, 1)
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;  // m_run: the reference max the exponentials are taken against
     for (int j = 0; j < ntiles; ++j) {
-      const int st = j & 1, ph = (j >> 1) & 1;
-      mbar_wait(&ctl->s_full[st], ph);
+      const int sb = j % CF::SBUFS, sph = (j / CF::SBUFS) & 1;
+      const int pb = j % CF::PBUFS;
+      mbar_wait(&ctl->s_full[sb], sph);
       fence_after_sync();
       const int kvalid = L - j * kKT - half * 64;  // keys >= kvalid of this thread's 64 are padding
       float mt = -INFINITY;
       uint32_t sreg[2][32];
+      const uint32_t s_addr = tm_s0 + sb * CF::S_COLS + lane_addr + half * 64;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tm_s0 + st * 128 + lane_addr + half * 64 + c * 32, sreg[c]);
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld_32x32b_x32(s_addr + c * 32, sreg[c]);
+        if (NSPLIT == 2) {
+          uint32_t sx[32];
+          tmem_ld_32x32b_x32(s_addr + 128 + c * 32, sx);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            sreg[c][i] = __float_as_uint(fmaf(__uint_as_float(sx[i]), 1.f / 2048.f, __uint_as_float(sreg[c][i])));
+        }
+      }
       tmem_ld_wait();
       fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ctl->s_empty[st]);
+      if (lane == 0) mbar_arrive(&ctl->s_empty[sb]);
 #pragma unroll
       for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(sreg[c][i]);
-          if (c * 32 + i >= kvalid) s = -INFINITY;
-          sreg[c][i] = __float_as_uint(s);
-          mt = fmaxf(mt, s);
+          float sv = __uint_as_float(sreg[c][i]);
+          if (c * 32 + i >= kvalid) sv = -INFINITY;
+          sreg[c][i] = __float_as_uint(sv);
+          mt = fmaxf(mt, sv);
         }
       // row max over both halves (the partner thread lives in another warp): smem + named barrier
       ctl->rowmax[j & 1][half][row] = mt;
@@ -245,26 +325,19 @@ __global__ void __launch_bounds__(kNlThreads, 1)
       float psum = 0.f;
       // O may only be rescaled once every PV product issued so far has landed (they complete in order)
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-        mbar_wait(&ctl->pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        mbar_wait(&ctl->pv_done[(j - 1) % CF::PBUFS], ((j - 1) / CF::PBUFS) & 1);
         fence_after_sync();
-        // this thread's half of the 96 O columns: 32 + 16
-        uint32_t o[32];
-        tmem_ld_32x32b_x32(tm_o + lane_addr + half * 48, o);
-        tmem_ld_wait();
+        // this thread's half of the 96 O columns (32 + 16), in every plane of O
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-        tmem_st_32x32b_x32(tm_o + lane_addr + half * 48, o);
-        uint32_t o2[16];
-        tmem_ld_32x32b_x16(tm_o + lane_addr + half * 48 + 32, o2);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) o2[i] = __float_as_uint(__uint_as_float(o2[i]) * alpha);
-        tmem_st_32x32b_x16(tm_o + lane_addr + half * 48 + 32, o2);
+        for (int pl = 0; pl < NSPLIT; ++pl) {
+          rescale_o32(tm_o + lane_addr + pl * kVR + half * 48, alpha);
+          rescale_o16(tm_o + lane_addr + pl * kVR + half * 48 + 32, alpha);
+        }
         tmem_st_wait();
       }
-      // this tile's P buffer was last read by the PV product of tile j-2
-      if (j >= 2) mbar_wait(&ctl->pv_done[st], ((j - 2) >> 1) & 1);
-      uint8_t* pbuf = p_sm + st * kPBytes;
+      // this tile's P buffer was last read by the PV product of tile j - PBUFS
+      if (j >= CF::PBUFS) mbar_wait(&ctl->pv_done[pb], ((j - CF::PBUFS) / CF::PBUFS) & 1);
+      uint8_t* pbuf = p_sm + pb * CF::P_BYTES;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
 #pragma unroll
@@ -287,7 +360,7 @@ __global__ void __launch_bounds__(kNlThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->p_ready);
     }
-    mbar_wait(&ctl->pv_done[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
+    mbar_wait(&ctl->pv_done[(ntiles - 1) % CF::PBUFS], ((ntiles - 1) / CF::PBUFS) & 1);
     fence_after_sync();
     // l of the row = sum of the two half-row sums (both were kept against the same reference max)
     ctl->rowsum[half][row] = l_run;
@@ -299,6 +372,19 @@ __global__ void __launch_bounds__(kNlThreads, 1)
       uint32_t o2[16];
       tmem_ld_32x32b_x32(tm_o + lane_addr + half * 48, o);
       tmem_ld_32x32b_x16(tm_o + lane_addr + half * 48 + 32, o2);
+      if (NSPLIT == 2) {
+        uint32_t ol[32];
+        uint32_t ol2[16];
+        tmem_ld_32x32b_x32(tm_o + lane_addr + kVR + half * 48, ol);
+        tmem_ld_32x32b_x16(tm_o + lane_addr + kVR + half * 48 + 32, ol2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          o[i] = __float_as_uint(fmaf(__uint_as_float(ol[i]), 1.f / 2048.f, __uint_as_float(o[i])));
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          o2[i] = __float_as_uint(fmaf(__uint_as_float(ol2[i]), 1.f / 2048.f, __uint_as_float(o2[i])));
+      }
       tmem_ld_wait();
       if (q < L) {
         float* dst = Y + ((long long)n * L + q) * kNL + half * 48;
@@ -321,11 +407,13 @@ __global__ void __launch_bounds__(kNlThreads, 1)
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-// X fp32 [N,L,84] -> X16 [N,Lp,128] (zero padded; Q and K) and Xt16 [N,96,Lp] = X^T (zero padded; V).
+// X fp32 [N,L,84] -> X16 [plane][N,Lp,128] (zero padded; Q and K) and Xt16 [plane][N,96,Lp] = X^T (zero padded; V);
+// plane 1 (nsplit = 2) holds (x - fp16(x)) * 2048.
 // V = X because the g linear is folded into the output linear: w(P*(X*Wg+bg)) = P*X*(Wg*Ww) + (bg*Ww+bw)
 // (softmax rows sum to 1; utils.py:26,64,67).  Pure cast + transpose, CTA = 64 tokens of one clip.
-__global__ void __launch_bounds__(256) nl_prep_kernel(const float* __restrict__ X, int L, int Lp,
-                                                      __half* __restrict__ X16, __half* __restrict__ Xt16) {
+__global__ void __launch_bounds__(256) nl_prep_kernel(const float* __restrict__ X, int L, int Lp, int nsplit,
+                                                      __half* __restrict__ X16, long long x_plane,
+                                                      __half* __restrict__ Xt16, long long xt_plane) {
   __shared__ float xs[64 * (kNL + 1)];
   const int tid = threadIdx.x;
   const int n = blockIdx.y, t0 = blockIdx.x * 64;
@@ -337,51 +425,67 @@ __global__ void __launch_bounds__(256) nl_prep_kernel(const float* __restrict__ 
   __syncthreads();
   for (int i = tid; i < 64 * kCP; i += 256) {   // X16 rows (coalesced 256-byte rows)
     const int tl = i / kCP, c = i % kCP;
-    X16[((long long)n * Lp + t0 + tl) * kCP + c] = __float2half_rn(c < kNL ? xs[tl * (kNL + 1) + c] : 0.f);
+    const float v = c < kNL ? xs[tl * (kNL + 1) + c] : 0.f;
+    const __half hi = __float2half_rn(v);
+    const long long o = ((long long)n * Lp + t0 + tl) * kCP + c;
+    X16[o] = hi;
+    if (nsplit == 2) X16[x_plane + o] = __float2half_rn((v - __half2float(hi)) * 2048.f);
   }
   for (int i = tid; i < kVR * 64; i += 256) {   // Xt16 rows (token-contiguous)
     const int c = i >> 6, tl = i & 63;
-    Xt16[((long long)n * kVR + c) * Lp + t0 + tl] = __float2half_rn(c < kNL ? xs[tl * (kNL + 1) + c] : 0.f);
+    const float v = c < kNL ? xs[tl * (kNL + 1) + c] : 0.f;
+    const __half hi = __float2half_rn(v);
+    const long long o = ((long long)n * kVR + c) * Lp + t0 + tl;
+    Xt16[o] = hi;
+    if (nsplit == 2) Xt16[xt_plane + o] = __float2half_rn((v - __half2float(hi)) * 2048.f);
   }
 }
 
-struct NlScratch {
-  __half* x16 = nullptr;
-  __half* gt16 = nullptr;
-  float* y = nullptr;
-  size_t cap_tokens = 0;  // N*Lp capacity
-};
+// bytes of the two operand arrays (always sized for two planes)
+size_t nl_x_bytes(int N, size_t Lp) { return (2 * (size_t)N * Lp * kCP * 2 + 1023) / 1024 * 1024; }
+size_t nl_g_bytes(int N, size_t Lp) { return (2 * (size_t)N * kVR * Lp * 2 + 1023) / 1024 * 1024; }
 
 }  // namespace
 
 bool tc_has_nonlocal() { return true; }
 
+// hi/lo-split operands where the convs are split too (fp32-grade path), fp16 operands otherwise
+int tc_nl_nsplit(int precision) { return precision == PFNL_PREC_TC_FP16X3 ? 2 : 1; }
+
 int tc_nl_init() {
-  PFNL_CUDA(cudaFuncSetAttribute(nl_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNlSmem));
+  PFNL_CUDA(cudaFuncSetAttribute(nl_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, NlCfg<1>::SMEM));
+  PFNL_CUDA(cudaFuncSetAttribute(nl_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, NlCfg<2>::SMEM));
   return PFNL_OK;
 }
 
-static int run_nl_tc(const float* tokens, int N, int L, __half* x16, __half* gt16, float* Y, cudaStream_t s) {
+static int run_nl_tc(const float* tokens, int N, int L, int nsplit, __half* x16, __half* gt16, float* Y,
+                     cudaStream_t s) {
   const int Lp = ceil_div(L, kKT) * kKT;
+  const long long x_plane = (long long)N * Lp * kCP, g_plane = (long long)N * kVR * Lp;
   dim3 pg(Lp / 64, N);
-  nl_prep_kernel<<<pg, 256, 0, s>>>(tokens, L, Lp, x16, gt16);
+  nl_prep_kernel<<<pg, 256, 0, s>>>(tokens, L, Lp, nsplit, x16, x_plane, gt16, g_plane);
   PFNL_LAUNCH_CHECK();
-  CUtensorMap tmx, tmg;
+  CUtensorMap tmx, tmxl, tmg, tmgl;
   int r = make_mat_tmap(&tmx, x16, (uint64_t)N * Lp, kCP, kQT);
+  if (r == 0) r = make_mat_tmap(&tmxl, x16 + (nsplit == 2 ? x_plane : 0), (uint64_t)N * Lp, kCP, kQT);
   if (r == 0) r = make_mat_tmap(&tmg, gt16, (uint64_t)N * kVR, (uint64_t)Lp, kVR);
+  if (r == 0) r = make_mat_tmap(&tmgl, gt16 + (nsplit == 2 ? g_plane : 0), (uint64_t)N * kVR, (uint64_t)Lp, kVR);
   if (r != 0) {
     set_error("non-local tensor map encode failed (%d)", r);
     return PFNL_ERR_CUDA;
   }
   dim3 grid(Lp / kQT, N);
-  nl_tc_kernel<<<grid, kNlThreads, kNlSmem, s>>>(tmx, tmg, L, Lp, Y);
+  if (nsplit == 2)
+    nl_tc_kernel<2><<<grid, kNlThreads, NlCfg<2>::SMEM, s>>>(tmx, tmxl, tmg, tmgl, L, Lp, Y);
+  else
+    nl_tc_kernel<1><<<grid, kNlThreads, NlCfg<1>::SMEM, s>>>(tmx, tmxl, tmg, tmgl, L, Lp, Y);
   PFNL_LAUNCH_CHECK();
   return PFNL_OK;
 }
 
 size_t tc_nl_workspace_bytes(int N, int L) {
   const size_t Lp = (size_t)ceil_div(L, kKT) * kKT;
-  return N * Lp * kCP * 2 + 1024 + (size_t)N * kVR * Lp * 2 + 1024;
+  return nl_x_bytes(N, Lp) + nl_g_bytes(N, Lp) + 1024;
 }
 
 int tc_nonlocal(const TcWeights& tw, TcWorkspace& w, const float* tokens, const float* lr, int N, int H, int W,
@@ -389,10 +493,10 @@ int tc_nonlocal(const TcWeights& tw, TcWorkspace& w, const float* tokens, const 
   const int L = (H / 2) * (W / 2);
   const size_t Lp = (size_t)ceil_div(L, kKT) * kKT;
   __half* x16 = (__half*)w.nl_x16;
-  __half* gt16 = (__half*)((uint8_t*)w.nl_x16 + (N * Lp * kCP * 2 + 1023) / 1024 * 1024);
+  __half* gt16 = (__half*)((uint8_t*)w.nl_x16 + nl_x_bytes(N, Lp));
   float* y = (float*)w.nl_priv;
   if (prof) prof->begin(kProfNonlocal, s);
-  int rc = run_nl_tc(tokens, N, L, x16, gt16, y, s);
+  int rc = run_nl_tc(tokens, N, L, tc_nl_nsplit(tw.precision), x16, gt16, y, s);
   if (rc == PFNL_OK) rc = launch_nl_linear_scatter(y, lr, N, H, W, tw.raw.nl_gw_w, tw.raw.nl_gw_b, inp21, s);
   if (prof) prof->end(s);
   if (rc) return rc;
@@ -406,8 +510,8 @@ int tc_nonlocal_tokens(const TcWeights& tw, const float* tokens, int N, int L, f
   static uint8_t* scratch = nullptr;
   static size_t cap = 0;
   const size_t Lp = (size_t)ceil_div(L, kKT) * kKT;
-  const size_t b_x = (N * Lp * kCP * 2 + 1023) / 1024 * 1024;
-  const size_t b_g = ((size_t)N * kVR * Lp * 2 + 1023) / 1024 * 1024;
+  const size_t b_x = nl_x_bytes(N, Lp);
+  const size_t b_g = nl_g_bytes(N, Lp);
   const size_t b_y = ((size_t)N * L * kNL * 4 + 1023) / 1024 * 1024;
   if (b_x + b_g + b_y > cap) {
     if (scratch) {
@@ -422,7 +526,7 @@ int tc_nonlocal_tokens(const TcWeights& tw, const float* tokens, int N, int L, f
   __half* x16 = (__half*)scratch;
   __half* gt16 = (__half*)(scratch + b_x);
   float* y = (float*)(scratch + b_x + b_g);
-  int rc = run_nl_tc(tokens, N, L, x16, gt16, y, s);
+  int rc = run_nl_tc(tokens, N, L, tc_nl_nsplit(tw.precision), x16, gt16, y, s);
   if (rc == PFNL_OK) rc = launch_nl_linear(y, N * L, tw.raw.nl_gw_w, tw.raw.nl_gw_b, out, s);
   if (rc) return rc;
   *launches += 3;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 #include <functional>
 #include <vector>
@@ -22,7 +23,11 @@ constexpr int kTcBaseOffsetMode = 0;
 inline int tc_nsplit(int precision) {
   return (precision == PFNL_PREC_TC_FP16X3 || precision == PFNL_PREC_TC_FP16X3_NLTC) ? 2 : 1;
 }
+// FP16X3 runs the non-local block on tcgen05 with hi/lo-split operands (PFNL_NL_FFMA=1 in the environment keeps
+// the fp32 CUDA-core kernel for A/B runs); FP16 and FP16X3_NLTC use fp16 operands.
 inline bool tc_nl_on_tensor_cores(int precision) {
+  static const bool ffma = getenv("PFNL_NL_FFMA") != nullptr;
+  if (precision == PFNL_PREC_TC_FP16X3) return !ffma;
   return precision == PFNL_PREC_TC_FP16 || precision == PFNL_PREC_TC_FP16X3_NLTC;
 }
 

@@ -1,5 +1,3 @@
 #!/bin/bash
-for n in 16 8 4; do
-echo "== clips $n"
-PFNL_TC_TRACE=1 timeout 120 python tools/tc_trace_test.py fp16x3 $n 2>&1 | tail -4 | cut -c1-330
-done
+timeout 300 python tools/gate_margin.py 2>&1 | grep -v CUDAEvent | tail -2
+PFNL_NL_FFMA=1 timeout 300 python tools/gate_margin.py 2>&1 | grep -v CUDAEvent | tail -2

@@ -132,6 +132,24 @@ def test_nonlocal_tcgen05_vs_oracle(tc_engines, hh, ww, n):
     assert err <= 4e-3
 
 
+@pytest.mark.parametrize("hh,ww,n", [(16, 16, 2), (10, 6, 2), (13, 10, 1), (32, 32, 1), (64, 64, 1), (1, 1, 1)])
+def test_nonlocal_tcgen05_split_operands_vs_oracle(tc_engines, hh, ww, n):
+    """The hi/lo-split tcgen05 non-local block of the fp16x3 mode (fp32-grade logits and values, fp16 P):
+    an order of magnitude closer to the fp64 oracle than the fp16-operand kernel."""
+    L = hh * ww
+    rng = np.random.default_rng(L)
+    W = R.make_weights("A")
+    x = rng.random((n, L, 84), dtype=np.float32)
+    got = tc_engines[("fp16x3", "A")].nonlocal_block(cu(x)).cpu().numpy()
+    P = "nlvsr/nlblock_0/"
+    ref = R.nonlocal_block(x.astype(np.float64).reshape(n, hh, ww, 84), W[P + "g/g/kernel"].astype(np.float64),
+                           W[P + "g/g/bias"].astype(np.float64), W[P + "w/w/kernel"].astype(np.float64),
+                           W[P + "w/w/bias"].astype(np.float64), stable=True).reshape(n, L, 84)
+    err = np.abs(got - ref).max()
+    print(f"tcgen05 split non-local L={L}: max-abs {err:.3e} (|ref|max {np.abs(ref).max():.2f})")
+    assert err <= 2.5e-4   # fp16 rounding of P (2^-12 relative per element); the fp16-operand kernel is at ~5e-4 to 8e-4
+
+
 def test_nonlocal_tcgen05_large_logits_and_6480(tc_engines):
     e = tc_engines[("fp16", "B")]
     W = R.make_weights("B")
