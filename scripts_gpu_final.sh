@@ -8,7 +8,7 @@ timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/$
 timeout 300 python tools/config_sweep.py > gpurun_out/${T}_config_sweep.json 2> gpurun_out/${T}_config_sweep.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches_fp16x3.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-alt > gpurun_out/${T}_ncu_bench.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 30 -c 2 -o gpurun_out/${T}_conv_tc -f python tools/dbg_forward.py fp16x3 eager > gpurun_out/${T}_ncu_conv.log 2>&1
-timeout 400 ncu --set full --clock-control none -k regex:nl_tc -s 6 -c 1 -o gpurun_out/${T}_nl_tc -f python tools/nl_one.py > gpurun_out/${T}_ncu_nl.log 2>&1
+timeout 400 ncu --set full --clock-control none -k regex:nl_tc -s 7 -c 2 -o gpurun_out/${T}_nl_tc -f python tools/nl_one.py > gpurun_out/${T}_ncu_nl.log 2>&1
 cat gpurun_out/${T}_pytest.log
 python - $T <<'PY'
 import json,sys
