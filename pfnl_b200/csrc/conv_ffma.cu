@@ -331,10 +331,10 @@ int launch_conv0(const float* inp21, int N, int H, int W, const float* w_hwio, c
 // One thread per out1 pixel (2H x 2W): reads large1 through the DCR index map (12 contiguous
 // floats of merge per tap), then writes its 2x2 HR pixels with the bicubic skip added.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) tail_kernel(const float* __restrict__ merge, const float* __restrict__ lr,
+__global__ void __launch_bounds__(128, 4) tail_kernel(const float* __restrict__ merge, const float* __restrict__ lr,
                                                    int N, int H, int W, const float* __restrict__ w2,
                                                    const float* __restrict__ b2, float* __restrict__ sr) {
-  __shared__ float wsm[9 * 12 * 12];
+  __shared__ __align__(16) float wsm[9 * 12 * 12];
   __shared__ float bsm[12];
   for (int i = threadIdx.x; i < 9 * 12 * 12; i += blockDim.x) wsm[i] = w2[i];
   if (threadIdx.x < 12) bsm[threadIdx.x] = b2[threadIdx.x];
@@ -362,11 +362,18 @@ __global__ void __launch_bounds__(128) tail_kernel(const float* __restrict__ mer
             merge + (((long long)n * H + (yy >> 1)) * W + (xx >> 1)) * 48 + (((yy & 1) << 1) + (xx & 1)) * 12);
         const float4 v0 = src[0], v1 = src[1], v2 = src[2];
         const float v[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
-        const float* wt = wsm + (dy * 3 + dx) * 144;
+        // 16-byte weight reads (one LDS.128 per 4 FMAs: the scalar version was bound by its 1296 LDS per thread)
+        const float4* wt = reinterpret_cast<const float4*>(wsm + (dy * 3 + dx) * 144);
 #pragma unroll
         for (int ci = 0; ci < 12; ++ci)
 #pragma unroll
-          for (int co = 0; co < 12; ++co) acc[co] = fmaf(v[ci], wt[ci * 12 + co], acc[co]);
+          for (int c4 = 0; c4 < 3; ++c4) {
+            const float4 w4 = wt[ci * 3 + c4];
+            acc[c4 * 4 + 0] = fmaf(v[ci], w4.x, acc[c4 * 4 + 0]);
+            acc[c4 * 4 + 1] = fmaf(v[ci], w4.y, acc[c4 * 4 + 1]);
+            acc[c4 * 4 + 2] = fmaf(v[ci], w4.z, acc[c4 * 4 + 2]);
+            acc[c4 * 4 + 3] = fmaf(v[ci], w4.w, acc[c4 * 4 + 3]);
+          }
       }
     }
     const float* centre = lr + ((long long)n * kFrames + kFrames / 2) * H * W * 3;

@@ -806,8 +806,9 @@ __global__ void __launch_bounds__(256, 2) conv0_planes_kernel(const float* __res
 // (dy,dx,c) padded to 80 = 5 k-steps; one CTA (128 threads = 128 tile pixels = 128 TMEM lanes) per 16x8
 // tile: stage the 20x12x3 fp32 patch, let every thread write its pixel's 80 operand values as hi/lo fp16
 // core-matrix rows (un-swizzled K-major: [k-chunk][row][8 k]), 5 x (N=128 + N=64) MMAs, epilogue as the
-// other convs.  ~65 KB of smem and 128 TMEM columns per CTA: three CTAs share an SM and overlap each
-// other's phases, which replaces an intra-CTA pipeline.
+// other convs.  ~65 KB of smem and 128 TMEM columns per CTA: three persistent CTAs share an SM (each keeps
+// its 20 KB weight image for all of its tiles) and overlap each other's phases, which replaces an
+// intra-CTA pipeline.
 template <int NSPLIT>
 struct Conv0Cfg {
   static constexpr int KC = 10;                       // k-chunks of 8
@@ -833,7 +834,7 @@ __global__ void pack_conv0_tc_kernel(const float* __restrict__ hwio, int nsplit,
 
 template <int NSPLIT>
 __global__ void __launch_bounds__(128) conv0_tc_kernel(const float* __restrict__ inp21, int H, int W, int tiles_x,
-                                                       int tiles_y, const __half* __restrict__ wimg,
+                                                       int tiles_y, int ntiles, const __half* __restrict__ wimg,
                                                        const float* __restrict__ bias, __half* __restrict__ out_hi,
                                                        __half* __restrict__ out_lo) {
   using CF = Conv0Cfg<NSPLIT>;
@@ -846,10 +847,6 @@ __global__ void __launch_bounds__(128) conv0_tc_kernel(const float* __restrict__
   uint64_t* bar = reinterpret_cast<uint64_t*>(bias_sm + 64);   // [0]: weights landed, [1]: MMAs done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int tile = blockIdx.x;
-  const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, img = tile / (tiles_x * tiles_y);
-  const int n = img / kFrames, t = img % kFrames;
-  const int y0 = ty * 16, x0 = tx * 8;
 
   if (tid == 0) {
     mbar_init(&bar[0], 1);
@@ -864,111 +861,119 @@ __global__ void __launch_bounds__(128) conv0_tc_kernel(const float* __restrict__
     tmem_relinquish();
   }
   if (tid < 64) bias_sm[tid] = bias[tid];
-  pdl_wait();  // inp21 is written by the previous kernel
-  {  // all loads in flight before the first store: the patch is the latency of this kernel
-    constexpr int NL = (CF::PATCH_FLOATS + 127) / 128;
-    float pv[NL];
-#pragma unroll
-    for (int u = 0; u < NL; ++u) {
-      const int i = tid + u * 128;
-      const int c = i % 3, pp = i / 3;
-      const int py = pp / 12, px = pp % 12;
-      const int gy = y0 + py - 2, gx = x0 + px - 2;
-      pv[u] = 0.f;
-      if (i < CF::PATCH_FLOATS && gy >= 0 && gy < H && gx >= 0 && gx < W)
-        pv[u] = inp21[(((long long)n * H + gy) * W + gx) * 21 + t * 3 + c];
-    }
-#pragma unroll
-    for (int u = 0; u < NL; ++u) {
-      const int i = tid + u * 128;
-      if (i < CF::PATCH_FLOATS) patch[i] = pv[u];
-    }
-  }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  // ---- im2col: this thread's pixel = tile row m; its 80 operand values, 8 per 16-byte core-matrix row
-  const int m = tid, my = m >> 3, mx = m & 7;
+  pdl_wait();  // inp21 is written by the previous kernel
+  const int m = tid, my = m >> 3, mx = m & 7;  // this thread's pixel = tile row m = TMEM lane
+  uint32_t done_par = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, done_par ^= 1u) {
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, img = tile / (tiles_x * tiles_y);
+    const int n = img / kFrames, t = img % kFrames;
+    const int y0 = ty * 16, x0 = tx * 8;
+    {  // all loads in flight before the first store: the patch is the latency of this kernel
+      constexpr int NL = (CF::PATCH_FLOATS + 127) / 128;
+      float pv[NL];
 #pragma unroll
-  for (int kc = 0; kc < CF::KC; ++kc) {
-    __align__(16) __half hh[8];
-    __align__(16) __half hl[8];
-#pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-      const int k = kc * 8 + kk;
-      float v = 0.f;
-      if (k < 75) {
-        const int tap = k / 3, c = k - tap * 3;
-        const int dy = tap / 5, dx = tap - dy * 5;
-        v = patch[((my + dy) * 12 + mx + dx) * 3 + c];
+      for (int u = 0; u < NL; ++u) {
+        const int i = tid + u * 128;
+        const int c = i % 3, pp = i / 3;
+        const int py = pp / 12, px = pp % 12;
+        const int gy = y0 + py - 2, gx = x0 + px - 2;
+        pv[u] = 0.f;
+        if (i < CF::PATCH_FLOATS && gy >= 0 && gy < H && gx >= 0 && gx < W)
+          pv[u] = inp21[(((long long)n * H + gy) * W + gx) * 21 + t * 3 + c];
       }
-      if (NSPLIT == 2)
-        split_half(v, hh[kk], hl[kk]);
-      else
-        hh[kk] = __float2half_rn(v);
-    }
-    *reinterpret_cast<uint4*>(a_sm + (kc * 128 + m) * 16) = *reinterpret_cast<const uint4*>(hh);
-    if (NSPLIT == 2)
-      *reinterpret_cast<uint4*>(a_sm + CF::A_BYTES + (kc * 128 + m) * 16) = *reinterpret_cast<const uint4*>(hl);
-  }
-  fence_proxy_async();  // generic-proxy operand writes -> visible to the tensor core (async proxy)
-  __syncthreads();
-  if (warp == 0) {
-    mbar_wait(&bar[0], 0);
-    fence_after_sync();
-    if (elect_one()) {
-      constexpr uint32_t idesc_hi = make_idesc_f16(128, NSPLIT * 64);
-      constexpr uint32_t idesc_lo = make_idesc_f16(128, 64);
-      // K-major, no swizzle: 8-row groups 128 B apart (SBO), the two k-chunks of a K=16 step LBO apart
-      const uint64_t ad = make_sdesc_interleave(smem_u32(a_sm), 128 * 16, 128);
-      const uint64_t bd = make_sdesc_interleave(smem_u32(b_sm), CF::B_ROWS * 16, 128);
 #pragma unroll
-      for (int ks = 0; ks < 5; ++ks)
-        mma_f16(tmem, ad + ((ks * 2 * 128 * 16) >> 4), bd + ((ks * 2 * CF::B_ROWS * 16) >> 4), idesc_hi, ks > 0);
-      if (NSPLIT == 2) {
-        const uint64_t al = make_sdesc_interleave(smem_u32(a_sm + CF::A_BYTES), 128 * 16, 128);
+      for (int u = 0; u < NL; ++u) {
+        const int i = tid + u * 128;
+        if (i < CF::PATCH_FLOATS) patch[i] = pv[u];
+      }
+    }
+    __syncthreads();
+    // ---- im2col: this thread's 80 operand values, 8 per 16-byte core-matrix row
+#pragma unroll
+    for (int kc = 0; kc < CF::KC; ++kc) {
+      __align__(16) __half hh[8];
+      __align__(16) __half hl[8];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const int k = kc * 8 + kk;
+        float v = 0.f;
+        if (k < 75) {
+          const int tap = k / 3, c = k - tap * 3;
+          const int dy = tap / 5, dx = tap - dy * 5;
+          v = patch[((my + dy) * 12 + mx + dx) * 3 + c];
+        }
+        if (NSPLIT == 2)
+          split_half(v, hh[kk], hl[kk]);
+        else
+          hh[kk] = __float2half_rn(v);
+      }
+      *reinterpret_cast<uint4*>(a_sm + (kc * 128 + m) * 16) = *reinterpret_cast<const uint4*>(hh);
+      if (NSPLIT == 2)
+        *reinterpret_cast<uint4*>(a_sm + CF::A_BYTES + (kc * 128 + m) * 16) = *reinterpret_cast<const uint4*>(hl);
+    }
+    fence_proxy_async();  // generic-proxy operand writes -> visible to the tensor core (async proxy)
+    fence_before_sync();  // the previous tile's tcgen05.ld are ordered before this tile's MMAs
+    __syncthreads();
+    if (warp == 0) {
+      fence_after_sync();
+      mbar_wait(&bar[0], 0);  // the weight image (first tile: may still be landing)
+      if (elect_one()) {
+        constexpr uint32_t idesc_hi = make_idesc_f16(128, NSPLIT * 64);
+        constexpr uint32_t idesc_lo = make_idesc_f16(128, 64);
+        // K-major, no swizzle: 8-row groups 128 B apart (SBO), the two k-chunks of a K=16 step LBO apart
+        const uint64_t ad = make_sdesc_interleave(smem_u32(a_sm), 128 * 16, 128);
+        const uint64_t bd = make_sdesc_interleave(smem_u32(b_sm), CF::B_ROWS * 16, 128);
 #pragma unroll
         for (int ks = 0; ks < 5; ++ks)
-          mma_f16(tmem + 64, al + ((ks * 2 * 128 * 16) >> 4), bd + ((ks * 2 * CF::B_ROWS * 16) >> 4), idesc_lo, 1u);
+          mma_f16(tmem, ad + ((ks * 2 * 128 * 16) >> 4), bd + ((ks * 2 * CF::B_ROWS * 16) >> 4), idesc_hi, ks > 0);
+        if (NSPLIT == 2) {
+          const uint64_t al = make_sdesc_interleave(smem_u32(a_sm + CF::A_BYTES), 128 * 16, 128);
+#pragma unroll
+          for (int ks = 0; ks < 5; ++ks)
+            mma_f16(tmem + 64, al + ((ks * 2 * 128 * 16) >> 4), bd + ((ks * 2 * CF::B_ROWS * 16) >> 4), idesc_lo, 1u);
+        }
+        mma_commit(&bar[1]);
       }
-      mma_commit(&bar[1]);
+      __syncwarp();
     }
-    __syncwarp();
+    mbar_wait(&bar[1], done_par);
+    fence_after_sync();
+    // ---- epilogue: thread = pixel (TMEM lane), 4 passes of 16 channels
+    const int y = y0 + my, x = x0 + mx;
+    const bool inb = y < H && x < W;
+    const long long cs = (long long)H * W * 8;
+    const uint32_t t0 = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      uint32_t d0[16], d1[16];
+      tmem_ld_32x32b_x16(t0 + c0, d0);
+      if (NSPLIT == 2) tmem_ld_32x32b_x16(t0 + 64 + c0, d1);
+      tmem_ld_wait();
+      U256 oh, ol;
+      __half* ph = reinterpret_cast<__half*>(&oh);
+      __half* pl = reinterpret_cast<__half*>(&ol);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float v = __uint_as_float(d0[j]);
+        if (NSPLIT == 2) v = fmaf(__uint_as_float(d1[j]), 1.f / 2048.f, v);
+        v = lrelu(v + bias_sm[c0 + j]);
+        if (NSPLIT == 2)
+          split_half(v, ph[j], pl[j]);
+        else
+          ph[j] = __float2half_rn(v);
+      }
+      if (inb) {
+        const long long poff = plane_off(img, c0 >> 3, y, x, H, W);
+        st_plane16(out_hi + poff, cs, oh);
+        if (NSPLIT == 2) st_plane16(out_lo + poff, cs, ol);
+      }
+    }
   }
   pdl_launch_dependents();
-  mbar_wait(&bar[1], 0);
-  fence_after_sync();
-  // ---- epilogue: thread = pixel (TMEM lane), 4 passes of 16 channels
-  const int y = y0 + my, x = x0 + mx;
-  const bool inb = y < H && x < W;
-  const long long cs = (long long)H * W * 8;
-  const uint32_t t0 = tmem + ((uint32_t)(warp * 32) << 16);
-#pragma unroll
-  for (int c0 = 0; c0 < 64; c0 += 16) {
-    uint32_t d0[16], d1[16];
-    tmem_ld_32x32b_x16(t0 + c0, d0);
-    if (NSPLIT == 2) tmem_ld_32x32b_x16(t0 + 64 + c0, d1);
-    tmem_ld_wait();
-    U256 oh, ol;
-    __half* ph = reinterpret_cast<__half*>(&oh);
-    __half* pl = reinterpret_cast<__half*>(&ol);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float v = __uint_as_float(d0[j]);
-      if (NSPLIT == 2) v = fmaf(__uint_as_float(d1[j]), 1.f / 2048.f, v);
-      v = lrelu(v + bias_sm[c0 + j]);
-      if (NSPLIT == 2)
-        split_half(v, ph[j], pl[j]);
-      else
-        ph[j] = __float2half_rn(v);
-    }
-    if (inb) {
-      const long long poff = plane_off(img, c0 >> 3, y, x, H, W);
-      st_plane16(out_hi + poff, cs, oh);
-      if (NSPLIT == 2) st_plane16(out_lo + poff, cs, ol);
-    }
-  }
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 128);
@@ -1334,7 +1339,8 @@ int trunk_tc(const TcWeights& tw, TcWorkspace& w, const float* inp21, int N, int
     const int tiles_x = ceil_div(W, 8), tiles_y = ceil_div(H, 16);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(tiles_x * tiles_y * N * kFrames);
+    const int ntiles = tiles_x * tiles_y * N * kFrames;
+    cfg.gridDim = dim3(ntiles < 3 * g_num_sms ? ntiles : 3 * g_num_sms);  // 3 CTAs per SM, each keeps its weights
     cfg.blockDim = dim3(128);
     cfg.dynamicSmemBytes = Conv0Cfg<NSPLIT>::SMEM;
     cfg.stream = s;
@@ -1347,7 +1353,7 @@ int trunk_tc(const TcWeights& tw, TcWorkspace& w, const float* inp21, int N, int
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    PFNL_CUDA(cudaLaunchKernelEx(&cfg, conv0_tc_kernel<NSPLIT>, inp21, H, W, tiles_x, tiles_y,
+    PFNL_CUDA(cudaLaunchKernelEx(&cfg, conv0_tc_kernel<NSPLIT>, inp21, H, W, tiles_x, tiles_y, ntiles,
                                  (const __half*)tw.conv0, tw.raw.conv0_b, (__half*)w.actA[0], (__half*)w.actA[1]));
   }
   if (prof) prof->end(s);
