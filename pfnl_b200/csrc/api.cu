@@ -253,13 +253,17 @@ int forward_launches(pfnl_handle* h, const float* lr, int N, int H, int W, float
   const int L = (H / 2) * (W / 2);
   const long long hw = (long long)H * W;
   int rc;
-  // tokens = space_to_depth(concat frames)                  pfnl.py:55-57
-  h->prof.begin(kProfPack, s);
-  rc = launch_pack_tokens(lr, N, H, W, w.tokens, s);
-  h->prof.end(s);
-  if (rc) return rc;
-  h->launches += 1;
-  if (tc_nl_on_tensor_cores(h->precision) && tc_has_nonlocal()) {
+  const bool nl_tc = tc_nl_on_tensor_cores(h->precision) && tc_has_nonlocal();
+  if (!nl_tc) {
+    // tokens = space_to_depth(concat frames)                pfnl.py:55-57
+    // (the tensor-core non-local path gathers them inside its operand-preparation kernel instead)
+    h->prof.begin(kProfPack, s);
+    rc = launch_pack_tokens(lr, N, H, W, w.tokens, s);
+    h->prof.end(s);
+    if (rc) return rc;
+    h->launches += 1;
+  }
+  if (nl_tc) {
     if ((rc = tc_nonlocal(h->tcw, w.tc, w.tokens, lr, N, H, W, w.inp21, s, &h->launches, &h->prof))) return rc;
   } else {
     h->prof.begin(kProfNonlocal, s);

@@ -139,7 +139,6 @@ struct TcCtrl {
   uint64_t wfull;        // weight image of the current phase has landed
   uint64_t wfree;        // all MMAs of the finished phase are complete (weights may be overwritten)
   uint64_t stores_done;  // all epilogue stores of the finished phase are globally visible
-  uint64_t peers_ready;  // every CTA of the cluster has finished phase 0 (weights may be multicast over)
   uint64_t full[8], empty[8];
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
@@ -221,19 +220,12 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// This CTA's share (1/cs) of a weight image: bulk copy L2 -> smem, multicast to every CTA of the cluster.
+// Whole weight image: linear bulk copies L2 -> smem (the image is stored pre-swizzled, UMMA-ready).
 template <int W_BYTES>
-__device__ __forceinline__ void load_weights_slice(uint8_t* wsm, const __half* wimg, uint64_t* wfull, uint32_t cs,
-                                                   uint32_t cr) {
-  const int slice = W_BYTES / (int)cs;  // W_BYTES is a multiple of 4 * 1024
-  const int beg = (int)cr * slice;
-  for (int off = beg; off < beg + slice; off += 32768) {
-    const int n = (beg + slice - off) < 32768 ? (beg + slice - off) : 32768;
-    if (cs > 1)
-      bulk_load_multicast(wsm + off, reinterpret_cast<const uint8_t*>(wimg) + off, n, wfull,
-                          (uint16_t)((1u << cs) - 1));
-    else
-      bulk_load(wsm + off, reinterpret_cast<const uint8_t*>(wimg) + off, n, wfull);
+__device__ __forceinline__ void load_weights(uint8_t* wsm, const __half* wimg, uint64_t* wfull) {
+  for (int off = 0; off < W_BYTES; off += 32768) {
+    const int n = (W_BYTES - off) < 32768 ? (W_BYTES - off) : 32768;
+    bulk_load(wsm + off, reinterpret_cast<const uint8_t*>(wimg) + off, n, wfull);
   }
 }
 
@@ -531,7 +523,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     mbar_init(&ctl->wfull, 1);
     mbar_init(&ctl->wfree, 1);
     mbar_init(&ctl->stores_done, kTcEpiWarps);
-    mbar_init(&ctl->peers_ready, cluster_nctarank());
     for (int i = 0; i < 8; ++i) {
       mbar_init(&ctl->full[i], 1);
       mbar_init(&ctl->empty[i], 1);
@@ -562,11 +553,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     tmem_alloc(&ctl->tmem_base, KC::TMEM_COLS);
     tmem_relinquish();
   }
-  // Weight images: each CTA of the cluster fetches 1/cs of the image from L2 and TMA-multicasts it
-  // into all cs CTAs (same smem offset, same mbarrier offset): L2->SM weight traffic drops cs-fold.
-  const uint32_t cs = cluster_nctarank(), cr = cluster_ctarank();
-  if (cs > 1) cluster_sync_all();  // every peer's barriers are initialised and wfull is armed
-  if (tid == 0) load_weights_slice<KC::W0>(wsm, ph0.wimg, &ctl->wfull, cs, cr);
+  if (tid == 0) load_weights<KC::W0>(wsm, ph0.wimg, &ctl->wfull);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -597,13 +584,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         if (early) producer_phase<P1, KC, NSPLIT>(ph, cm, ring, ctl, rg, tcount, 0, 1);
         mbar_wait(&ctl->wfree, (pi - 1) & 1);
         mbar_arrive_expect_tx(&ctl->wfull, KC::W1);
-        if (cs > 1) {
-          // peers may only overwrite my weights once I am done with the previous phase (and vice versa):
-          // tell every CTA of the cluster that I am ready, then wait until all of them are
-          for (uint32_t r = 0; r < cs; ++r) mbar_arrive_remote(&ctl->peers_ready, r);
-          mbar_wait_cluster(&ctl->peers_ready, (pi - 1) & 1);
-        }
-        load_weights_slice<KC::W1>(wsm, ph.wimg, &ctl->wfull, cs, cr);  // needs only the MMAs to have drained
+        load_weights<KC::W1>(wsm, ph.wimg, &ctl->wfull);  // needs only the MMAs to have drained
         if (cm.phase1_reads_phase0) {
           // this phase's patches are the CTA's own outputs of the previous phase (conv10 <- conv1): the
           // generic-proxy stores must be visible to the TMA (async proxy) first
@@ -647,7 +628,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, KC::TMEM_COLS);
   if (cm.trace != nullptr && tid == 0) cm.trace[193 + 2 * blockIdx.x] = globaltimer_ns();
-  if (cs > 1) cluster_sync_all();  // no CTA leaves while a peer's multicast may still target the cluster
 }
 
 // ---- weight images ------------------------------------------------------------------------------------
@@ -1022,58 +1002,17 @@ int launch_tc(const TcProgram& prog, int nphases, bool phase1_reads_phase0, int 
       return PFNL_ERR_BAD_ARG;
     }
   int grid = a.n_units < g_num_sms ? a.n_units : g_num_sms;
-  // Cluster size for the weight multicast: the largest of 4/2/1 for which the whole persistent grid is
-  // co-resident (1 CTA per SM; 4-CTA clusters fit 132 of the 148 SMs, pairs fit all 148).
-  static int max_clusters[5] = {0, 0, -1, 0, -1};  // per kernel instantiation, indexed by cluster size
-  static const int cs_limit = getenv("PFNL_TC_CLUSTER") ? atoi(getenv("PFNL_TC_CLUSTER")) : 1;  // measured on B200: clusters cost more (scheduling, handshake) than the multicast saves
-  int cs = 1;
-  for (int c = 4; c >= 2; c >>= 1) {
-    if (c > cs_limit) continue;
-    if (max_clusters[c] < 0) {
-      cudaLaunchConfig_t q;
-      memset(&q, 0, sizeof(q));
-      q.gridDim = dim3(g_num_sms / c * c);
-      q.blockDim = dim3(kTcThreads);
-      q.dynamicSmemBytes = KC::SMEM_BYTES;
-      cudaLaunchAttribute qa[1];
-      qa[0].id = cudaLaunchAttributeClusterDimension;
-      qa[0].val.clusterDim.x = c;
-      qa[0].val.clusterDim.y = 1;
-      qa[0].val.clusterDim.z = 1;
-      q.attrs = qa;
-      q.numAttrs = 1;
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<P0, P1, NSPLIT>, &q) != cudaSuccess) {
-        cudaGetLastError();
-        n = 0;
-      }
-      max_clusters[c] = n;
-    }
-    const int g = grid / c * c;
-    if (g >= c && g <= max_clusters[c] * c && (g == grid || g * 8 >= grid * 7)) {  // give up < 1/8 of the CTAs
-      cs = c;
-      grid = g;
-      break;
-    }
-  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = KC::SMEM_BYTES;
   cfg.stream = s;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
   int na = 0;
   if (pdl_enabled()) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
-  }
-  if (cs > 1) {
-    attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = cs;
-    attr[na].val.clusterDim.y = 1;
-    attr[na].val.clusterDim.z = 1;
     ++na;
   }
   cfg.attrs = attr;

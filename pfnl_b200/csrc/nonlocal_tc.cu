@@ -411,16 +411,36 @@ __global__ void __launch_bounds__(kNlThreads, 1)
 // plane 1 (nsplit = 2) holds (x - fp16(x)) * 2048.
 // V = X because the g linear is folded into the output linear: w(P*(X*Wg+bg)) = P*X*(Wg*Ww) + (bg*Ww+bw)
 // (softmax rows sum to 1; utils.py:26,64,67).  Pure cast + transpose, CTA = 64 tokens of one clip.
-__global__ void __launch_bounds__(256) nl_prep_kernel(const float* __restrict__ X, int L, int Lp, int nsplit,
-                                                      __half* __restrict__ X16, long long x_plane,
-                                                      __half* __restrict__ Xt16, long long xt_plane) {
+// With `lr` given (the forward path) the tokens are gathered straight from the LR clip - frame concat +
+// space_to_depth(.,2), model/pfnl.py:55-57: channel (dy*2+dx)*21 + t*3 + c of token (h2,w2) is
+// lr[n,t,2*h2+dy,2*w2+dx,c] - so the fp32 token matrix is never written (X is ignored).
+__global__ void __launch_bounds__(256) nl_prep_kernel(const float* __restrict__ X, const float* __restrict__ lr, int H,
+                                                      int W, int L, int Lp, int nsplit, __half* __restrict__ X16,
+                                                      long long x_plane, __half* __restrict__ Xt16,
+                                                      long long xt_plane) {
   __shared__ float xs[64 * (kNL + 1)];
   const int tid = threadIdx.x;
   const int n = blockIdx.y, t0 = blockIdx.x * 64;
-  const float* Xn = X + (long long)n * L * kNL;
-  for (int i = tid; i < 64 * kNL; i += 256) {
-    const int tl = i / kNL, c = i - tl * kNL;
-    xs[tl * (kNL + 1) + c] = (t0 + tl) < L ? Xn[(long long)t0 * kNL + i] : 0.f;
+  if (lr != nullptr) {
+    const int W2 = W >> 1;
+    for (int i = tid; i < 64 * kNL; i += 256) {
+      const int tl = i / kNL, ch = i - tl * kNL;
+      const int tok = t0 + tl;
+      float v = 0.f;
+      if (tok < L) {
+        const int h2 = tok / W2, w2 = tok - h2 * W2;
+        const int q = ch / 21, rr = ch - q * 21;
+        const int t = rr / 3, c = rr - t * 3;
+        v = lr[((((long long)n * kFrames + t) * H + 2 * h2 + (q >> 1)) * W + 2 * w2 + (q & 1)) * 3 + c];
+      }
+      xs[tl * (kNL + 1) + ch] = v;
+    }
+  } else {
+    const float* Xn = X + (long long)n * L * kNL;
+    for (int i = tid; i < 64 * kNL; i += 256) {
+      const int tl = i / kNL, c = i - tl * kNL;
+      xs[tl * (kNL + 1) + c] = (t0 + tl) < L ? Xn[(long long)t0 * kNL + i] : 0.f;
+    }
   }
   __syncthreads();
   for (int i = tid; i < 64 * kCP; i += 256) {   // X16 rows (coalesced 256-byte rows)
@@ -458,12 +478,13 @@ int tc_nl_init() {
   return PFNL_OK;
 }
 
-static int run_nl_tc(const float* tokens, int N, int L, int nsplit, __half* x16, __half* gt16, float* Y,
-                     cudaStream_t s) {
+// `lr` != NULL: gather the tokens from the LR clip [N,7,H,W,3] (L = H/2 * W/2), `tokens` unused
+static int run_nl_tc(const float* tokens, const float* lr, int H, int W, int N, int L, int nsplit, __half* x16,
+                     __half* gt16, float* Y, cudaStream_t s) {
   const int Lp = ceil_div(L, kKT) * kKT;
   const long long x_plane = (long long)N * Lp * kCP, g_plane = (long long)N * kVR * Lp;
   dim3 pg(Lp / 64, N);
-  nl_prep_kernel<<<pg, 256, 0, s>>>(tokens, L, Lp, nsplit, x16, x_plane, gt16, g_plane);
+  nl_prep_kernel<<<pg, 256, 0, s>>>(tokens, lr, H, W, L, Lp, nsplit, x16, x_plane, gt16, g_plane);
   PFNL_LAUNCH_CHECK();
   CUtensorMap tmx, tmxl, tmg, tmgl;
   int r = make_mat_tmap(&tmx, x16, (uint64_t)N * Lp, kCP, kQT);
@@ -496,7 +517,7 @@ int tc_nonlocal(const TcWeights& tw, TcWorkspace& w, const float* tokens, const 
   __half* gt16 = (__half*)((uint8_t*)w.nl_x16 + nl_x_bytes(N, Lp));
   float* y = (float*)w.nl_priv;
   if (prof) prof->begin(kProfNonlocal, s);
-  int rc = run_nl_tc(tokens, N, L, tc_nl_nsplit(tw.precision), x16, gt16, y, s);
+  int rc = run_nl_tc(nullptr, lr, H, W, N, L, tc_nl_nsplit(tw.precision), x16, gt16, y, s);
   if (rc == PFNL_OK) rc = launch_nl_linear_scatter(y, lr, N, H, W, tw.raw.nl_gw_w, tw.raw.nl_gw_b, inp21, s);
   if (prof) prof->end(s);
   if (rc) return rc;
@@ -526,7 +547,7 @@ int tc_nonlocal_tokens(const TcWeights& tw, const float* tokens, int N, int L, f
   __half* x16 = (__half*)scratch;
   __half* gt16 = (__half*)(scratch + b_x);
   float* y = (float*)(scratch + b_x + b_g);
-  int rc = run_nl_tc(tokens, N, L, tc_nl_nsplit(tw.precision), x16, gt16, y, s);
+  int rc = run_nl_tc(tokens, nullptr, 0, 0, N, L, tc_nl_nsplit(tw.precision), x16, gt16, y, s);
   if (rc == PFNL_OK) rc = launch_nl_linear(y, N * L, tw.raw.nl_gw_w, tw.raw.nl_gw_b, out, s);
   if (rc) return rc;
   *launches += 3;
