@@ -583,8 +583,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const bool early = !cm.phase1_reads_phase0;
         if (early) producer_phase<P1, KC, NSPLIT>(ph, cm, ring, ctl, rg, tcount, 0, 1);
         mbar_wait(&ctl->wfree, (pi - 1) & 1);
+        TC_TRACE(0, 32 + pi);
         mbar_arrive_expect_tx(&ctl->wfull, KC::W1);
         load_weights<KC::W1>(wsm, ph.wimg, &ctl->wfull);  // needs only the MMAs to have drained
+        TC_TRACE(0, 40 + pi);
         if (cm.phase1_reads_phase0) {
           // this phase's patches are the CTA's own outputs of the previous phase (conv10 <- conv1): the
           // generic-proxy stores must be visible to the TMA (async proxy) first
@@ -607,6 +609,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       __syncwarp();
       mbar_wait(&ctl->wfull, pi & 1);
       fence_after_sync();
+      if (lane == 0) TC_TRACE(1, 40 + pi);
       mma_phase<P1, KC, NSPLIT>(prog.ph[pi], cm, wsm, ring, ctl, tmem, rg, it, lane);
     }
   } else {
@@ -1041,6 +1044,8 @@ int launch_tc(const TcProgram& prog, int nphases, bool phase1_reads_phase0, int 
     fprintf(stderr, "\n  mma: weights ready %lld ; per tile (data ready, issue done):", t[64] - t0);
     for (int i = 0; i < 12 && t[64 + 1 + 2 * i]; ++i)
       fprintf(stderr, " (%lld,%lld)", t[64 + 1 + 2 * i] - t0, t[64 + 2 + 2 * i] - t0);
+    fprintf(stderr, "\n  swap to phase 1: MMAs drained %lld, image issued %lld, image landed %lld", t[33] - t0, t[41] - t0,
+            t[64 + 41] - t0);
     fprintf(stderr, "\n  epilogue per tile (acc ready, done):");
     for (int i = 0; i < 12 && t[128 + 2 * i]; ++i)
       fprintf(stderr, " (%lld,%lld)", t[128 + 2 * i] - t0, t[128 + 1 + 2 * i] - t0);
