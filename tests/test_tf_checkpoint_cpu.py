@@ -156,3 +156,40 @@ def test_pfnl_load_and_save_like_base_model(tmp_path, capsys, built_lib):
     T.write_checkpoint_state(str(tmp_path / "bad"), "VSR-1")
     with pytest.raises(KeyError):
         PFNL().load(str(tmp_path / "bad"))
+
+
+def test_varint_and_table_roundtrip_property():
+    """Random keys / values through the SSTable writer and reader (hypothesis): sorted output, every pair
+    intact, for block sizes that force one entry per block as well as one block in total."""
+    from hypothesis import given, settings, strategies as st
+    import tempfile
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.dictionaries(st.binary(min_size=0, max_size=40), st.binary(min_size=0, max_size=300), max_size=60),
+           st.sampled_from([1, 64, 4096, 1 << 20]))
+    def run(d, block_size):
+        items = list(d.items())
+        with tempfile.TemporaryDirectory() as tmp:
+            p = os.path.join(tmp, "t.index")
+            T.write_table(p, items, block_size=block_size)
+            assert T.read_table(p) == sorted(items)
+
+    run()
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(min_value=0, max_value=(1 << 64) - 1))
+    def varint(v):
+        b = T._put_varint(v)
+        assert T._get_varint(b + b"\xff", 0) == (v, len(b)) and len(b) <= 10
+
+    varint()
+
+
+def test_bundle_rejects_foreign_files(tmp_path):
+    p = tmp_path / "x.index"
+    p.write_bytes(b"not a table")
+    with pytest.raises(ValueError):
+        T.read_table(str(p))
+    p.write_bytes(bytes(100))
+    with pytest.raises(ValueError, match="magic"):
+        T.read_table(str(p))
