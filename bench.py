@@ -48,18 +48,44 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock and throttle reasons DURING the timed region: NVML polled every ~2 ms from a thread
+    (the device-resident loop lasts only tens of milliseconds), nvidia-smi -lms as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # NVML clocks-event (throttle) reason bits
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.rows = []
+        self.rows = []        # nvidia-smi fallback rows
+        self.samples = []     # (perf_counter, sm_mhz, reason_bits) from NVML
         self.proc = None
         self.thread = None
+        self.nvml = None
+        self.handle = None
+        self.max_mhz = None
+        self.stop_flag = False
+        self.window = None    # (t0, t1) of the timed region, set by mark()
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.idx
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:   # NVML indexes physical devices
+                ids = [v for v in vis.split(",") if v.strip() != ""]
+                if idx < len(ids) and ids[idx].strip().isdigit():
+                    idx = int(ids[idx])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
@@ -70,13 +96,45 @@ class ClockSampler:
         self.thread = threading.Thread(target=self._read, daemon=True)
         self.thread.start()
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((time.perf_counter(), mhz, bits))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             f = [x.strip() for x in line.split(",")]
             if len(f) >= 9:
                 self.rows.append(f)
 
+    def mark(self, t0, t1):
+        """perf_counter bounds of the timed (device-resident) loop."""
+        self.window = (t0, t1)
+
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            inside = [x for x in self.samples if self.window and self.window[0] <= x[0] <= self.window[1]]
+            use = inside if len(inside) >= 3 else self.samples
+            if not use:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no NVML samples"], "samples": 0}
+            bits = 0
+            for x in use:
+                bits |= x[2]
+            reasons = sorted(k for k, b in self.BITS.items() if bits & b)
+            return {"sm_mhz": statistics.median(x[1] for x in use), "sm_min_mhz": min(x[1] for x in use),
+                    "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(use),
+                    "samples_in_timed_region": len(inside), "source": "nvml, 2 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -98,7 +156,7 @@ class ClockSampler:
         # "under load" = samples within 25% of the highest clock seen (idle samples are excluded)
         load = [s for s in sm if s >= 0.5 * max(sm)] if sm else []
         return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 200"}
 
 
 def effective_cpus():
@@ -230,6 +288,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     barrier()
     wall_total = time.perf_counter() - wall0
+    sampler.mark(wall0, wall0 + wall_total)
     launches = eng.launches - l0
     step_ms = [a.elapsed_time(b) for a, b in evs]
     ms_dev = D.max_over_ranks(sum(step_ms) / K, device=dev)
