@@ -360,26 +360,33 @@ def read_bundle(prefix, names=None, verify_crc=True):
     want = list(entries) if names is None else list(names)
     shards = {}
     out = {}
-    for name in want:
-        if name not in entries:
-            raise KeyError(f"variable '{name}' not found in checkpoint {prefix}")
-        e = entries[name]
-        if e["slices"]:
-            raise ValueError(f"variable '{name}' is stored as partitioned slices: not supported")
-        dt = _DT.get(e["dtype"])
-        if dt is None:
-            raise ValueError(f"variable '{name}': unsupported dtype enum {e['dtype']}")
-        sid = e["shard_id"]
-        if sid not in shards:
-            shards[sid] = np.memmap(_data_path(prefix, sid, header["num_shards"]), dtype=np.uint8, mode="r")
-        raw = shards[sid][e["offset"]:e["offset"] + e["size"]]
-        count = int(np.prod(e["shape"], dtype=np.int64)) if e["shape"] else 1
-        if count * np.dtype(dt).itemsize != e["size"]:
-            raise ValueError(f"variable '{name}': size {e['size']} does not match shape {e['shape']}")
-        b = raw.tobytes()
-        if verify_crc and e["crc32c"] is not None and unmask_crc(e["crc32c"]) != crc32c(b):
-            raise ValueError(f"variable '{name}': data checksum mismatch")
-        out[name] = np.frombuffer(b, dtype=dt).reshape(e["shape"]).copy()
+    try:
+        for name in want:
+            if name not in entries:
+                raise KeyError(f"variable '{name}' not found in checkpoint {prefix}")
+            e = entries[name]
+            if e["slices"]:
+                raise ValueError(f"variable '{name}' is stored as partitioned slices: not supported")
+            dt = _DT.get(e["dtype"])
+            if dt is None:
+                raise ValueError(f"variable '{name}': unsupported dtype enum {e['dtype']}")
+            sid = e["shard_id"]
+            if sid not in shards:
+                shards[sid] = open(_data_path(prefix, sid, header["num_shards"]), "rb")
+            count = int(np.prod(e["shape"], dtype=np.int64)) if e["shape"] else 1
+            if count * np.dtype(dt).itemsize != e["size"]:
+                raise ValueError(f"variable '{name}': size {e['size']} does not match shape {e['shape']}")
+            f = shards[sid]
+            f.seek(e["offset"])
+            b = f.read(e["size"])
+            if len(b) != e["size"]:
+                raise ValueError(f"variable '{name}': data file truncated")
+            if verify_crc and e["crc32c"] is not None and unmask_crc(e["crc32c"]) != crc32c(b):
+                raise ValueError(f"variable '{name}': data checksum mismatch")
+            out[name] = np.frombuffer(b, dtype=dt).reshape(e["shape"]).copy()
+    finally:
+        for f in shards.values():
+            f.close()
     return out
 
 
