@@ -27,8 +27,10 @@
 // swizzle phase constrains the shift.
 // Weights ([taps][N][64] fp16, pre-swizzled) are resident in smem while a phase runs.
 //
-// One launch runs up to two PHASES back to back on the same persistent CTAs, swapping the weight
-// image in smem between them:   conv1 -> conv10   and   conv2(base half, fp32 partial) -> conv2(frame half).
+// One launch runs several PHASES back to back on the same persistent CTAs, swapping the weight image
+// in smem between them:   conv1 -> conv10,   conv2(base half, fp32 partial) -> conv2(frame half),   and the
+// 7 frame slices of convmerge1.  Everything that enters shared memory goes through one TMA queue, so the
+// first patch of a phase whose inputs do not depend on the previous one is issued BEFORE the weight swap.
 // A work unit is one spatial tile x 7 frames, and a CTA owns the same units in both phases, so the
 // phase-2 inputs that phase 1 produced are the CTA's own writes (conv10 reads the 7 conv1 tiles of
 // its unit; the frame half adds the partial sums its own threads stored).  This halves the launch
@@ -38,8 +40,8 @@
 // Warp roles (576 threads, 1 CTA / SM, persistent): warp 0 = TMA producer, warp 1 = MMA issuer
 // (converged warp, one elected lane issues; descriptors advance by constant adds), warps 2-17 =
 // epilogue (16 warps: 4 TMEM lane quarters x 4 sixteen-channel chunks; tcgen05.ld -> bias /
-// leaky_relu / partial sums / residual -> fp16 planes or fp32, 256-bit global accesses, operands
-// prefetched before the accumulator wait).  TMEM accumulators are double buffered.  Programmatic
+// leaky_relu / partial sums / residual -> fp16 planes (16-byte accesses, 4 full lines per warp
+// instruction) or fp32, operands prefetched before the accumulator wait).  TMEM accumulators are double buffered.  Programmatic
 // dependent launch overlaps the prologue with the previous kernel's tail.
 #include <cuda_fp16.h>
 
