@@ -94,6 +94,11 @@ class Engine:
         if ndim is not None and t.dim() != ndim:
             raise ValueError(f"expected {ndim} dims, got {tuple(t.shape)}")
 
+    def _chk_out(self, t, shape):
+        self._chk_in(t)
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"out must have shape {tuple(shape)}, got {tuple(t.shape)}")
+
     @property
     def launches(self):
         return int(lib.pfnl_launch_count(self._h))
@@ -126,6 +131,8 @@ class Engine:
             raise ValueError(f"input must be [N,7,H,W,3], got {tuple(x.shape)}")
         if out is None:
             out = torch.empty((n, 1, h * 4, w * 4, 3), dtype=torch.float32, device=self.device)
+        else:
+            self._chk_out(out, (n, 1, h * 4, w * 4, 3))
         check(lib.pfnl_forward(self._h, _ptr(x), n, h, w, _ptr(out), _stream_ptr(self.device)))
         return out
 
@@ -137,6 +144,9 @@ class Engine:
             raise ValueError(f"input must be [N,7,H,W,3], got {tuple(xt.shape)}")
         if out is None:
             out = torch.empty((n, 1, h * 4, w * 4, 3), dtype=torch.float32)
+        elif not (isinstance(out, torch.Tensor) and not out.is_cuda and out.dtype == torch.float32
+                  and out.is_contiguous() and tuple(out.shape) == (n, 1, h * 4, w * 4, 3)):
+            raise ValueError(f"out must be a contiguous float32 CPU tensor of shape {(n, 1, h * 4, w * 4, 3)}")
         with torch.cuda.device(self.device):
             check(lib.pfnl_forward_host(self._h, C.c_void_p(xt.data_ptr()), n, h, w, C.c_void_p(out.data_ptr()),
                                         _stream_ptr(self.device)))
@@ -145,6 +155,10 @@ class Engine:
     def mse(self, sr, hr):
         self._chk_in(sr, 5)
         self._chk_in(hr, 5)
+        # the reference's (SR - H)**2 (pfnl.py:90) would broadcast or raise on a shape mismatch; the kernel reads
+        # both tensors with sr's extent, so anything but equal [N,1,4H,4W,3] shapes is rejected here
+        if sr.shape != hr.shape or sr.shape[1] != 1 or sr.shape[-1] != 3:
+            raise ValueError(f"sr and hr must both be [N,1,4H,4W,3]; got {tuple(sr.shape)} and {tuple(hr.shape)}")
         n, _, h4, w4, _ = sr.shape
         out = torch.empty((n,), dtype=torch.float32, device=self.device)
         check(lib.pfnl_mse(self._h, _ptr(sr), _ptr(hr), n, h4, w4, _ptr(out), _stream_ptr(self.device)))
