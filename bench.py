@@ -333,9 +333,14 @@ def run_ours(args):
     if tc:
         # tensor-core path: two persistent launches per block -
         #   "conv1_3x3" = conv1 + conv10 (2A + A + B), "conv2_3x3" = base-half partial sums + frame half (+ residual)
+        #   "pfrb_flow" = the whole 20-block stack as one persistent dataflow kernel (pfrb_flow.cu): SURVEY 8d's
+        #   layer-granular bytes 20 x (2A + (A+B) + (3A+B)); the fp32 partial sums of the conv2 base/frame split are
+        #   the kernel's own scratch and are NOT counted as algorithmic bytes
         kinds = {
             "conv1_3x3": {"bytes": (3 * A_el + B_el) * act_bytes, "flops": f_conv1 + f_conv10},
-            "conv2_3x3": {"bytes": (3 * A_el + B_el) * act_bytes + 2 * B_el * 4, "flops": f_conv1 + f_pbase},
+            "conv2_3x3": {"bytes": (3 * A_el + B_el) * act_bytes, "flops": f_conv1 + f_pbase},
+            "pfrb_flow": {"bytes": 20 * (6 * A_el + 2 * B_el) * act_bytes,
+                          "flops": 20 * (2 * f_conv1 + f_conv10 + f_pbase)},
         }
     else:
         kinds = {

@@ -106,6 +106,19 @@ size_t pfnl_workspace_bytes(int precision, int N, int H, int W);
 int pfnl_reserve(pfnl_handle* h, int N, int H, int W);
 /* 1: pfnl_forward replays a cached CUDA graph per (N,H,W) shape; 0: plain launches. */
 int pfnl_set_graphs(pfnl_handle* h, int enable);
+/* Tensor-core precisions only.  1 (default): the 20 PFRBs (model/pfnl.py:65-71) run as ONE persistent dataflow
+ * kernel (csrc/pfrb_flow.cu); 0: two launches per block (csrc/conv_tc.cu).  Same arithmetic, bit-identical
+ * results; kept switchable for A/B measurements and tests.  PFNL_TC_FLOW=0 in the environment sets the default. */
+int pfnl_set_flow(pfnl_handle* h, int enable);
+/* Debugging aid.  Every device-side wait of the tensor-core kernels is bounded; the first one that gives up records
+ * {1 + kind, CTA, detail, detail} in host-mapped memory before it traps (the launch then fails with a CUDA error).
+ * Readable even after the context is lost.  kind 0: mbarrier (detail = smem address, parity); 1-4: a producer of the
+ * PFRB dataflow kernel waiting for the inputs of (block, item) in role kind-1; 5: its conv2 epilogue. */
+int pfnl_debug_fault(int* out4);
+/* With PFNL_FLOW_DEBUG=1 every CTA of the PFRB dataflow kernel keeps 8 ints of progress marks in host-mapped memory
+ * ([0..2] producer: state, block, item; [3] MMA warp: tiles issued; [4..6] epilogue: state, block, item; [7] role):
+ * copies the first n ints (n <= 2048).  Slow; for post-mortems of a timed-out wait only. */
+int pfnl_debug_progress(int* out, int n);
 
 /* Replaces: sess.run(SR_test, feed_dict={L_test: lr}) -> PFNL.forward, model/pfnl.py:39-80.
  *   lr_dev [N,7,H,W,3] -> sr_dev [N,1,4H,4W,3]; H and W even. */
@@ -165,6 +178,12 @@ int pfnl_bicubic4(pfnl_handle* h, const float* in_dev, int N, int H, int W, int 
  * weights, in the handle's precision: frames [N*7,H,W,64] fp32 -> frames_out (may alias). */
 int pfnl_pfrb(pfnl_handle* h, int blk, const float* frames_dev, int N, int H, int W,
               float* frames_out_dev, void* stream);
+/* conv0 = Conv2D(64, 5, 'same', leaky_relu) applied to each of the 7 frames (model/pfnl.py:48,61-62), in the
+ * handle's precision: inp21 [N,H,W,21] fp32 (frame t = channels 3t..3t+2) -> frames_out [N*7,H,W,64] fp32. */
+int pfnl_conv0(pfnl_handle* h, const float* inp21_dev, int N, int H, int W, float* frames_out_dev, void* stream);
+/* convmerge1 = Conv2D(48, 3, 'same', leaky_relu) over the channel concat of the 7 frames (model/pfnl.py:52,73-74),
+ * in the handle's precision: frames [N*7,H,W,64] fp32 -> merge [N,H,W,48] fp32. */
+int pfnl_convmerge1(pfnl_handle* h, const float* frames_dev, int N, int H, int W, float* merge_dev, void* stream);
 
 /* ---- the steps around the hot path in test_video_truth / test_video_lr ---- */
 

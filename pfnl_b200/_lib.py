@@ -58,6 +58,9 @@ SYMBOLS = {
     "pfnl_workspace_bytes": (C.c_size_t, [_I, _I, _I, _I]),
     "pfnl_reserve": (_I, [_VP, _I, _I, _I]),
     "pfnl_set_graphs": (_I, [_VP, _I]),
+    "pfnl_set_flow": (_I, [_VP, _I]),
+    "pfnl_debug_fault": (_I, [C.POINTER(C.c_int)]),
+    "pfnl_debug_progress": (_I, [C.POINTER(C.c_int), _I]),
     "pfnl_forward": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
     "pfnl_forward_host": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
     "pfnl_mse": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP, _VP]),
@@ -71,6 +74,8 @@ SYMBOLS = {
     "pfnl_conv2d_nhwc": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP, _VP, _VP]),
     "pfnl_bicubic4": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _VP]),
     "pfnl_pfrb": (_I, [_VP, _I, _VP, _I, _I, _I, _VP, _VP]),
+    "pfnl_conv0": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
+    "pfnl_convmerge1": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
     "pfnl_downsample4": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP, _VP]),
     "pfnl_gather_windows": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP, _VP]),
     "pfnl_quantize_u8": (_I, [_VP, _VP, C.c_longlong, _VP, _VP]),

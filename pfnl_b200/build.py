@@ -20,7 +20,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpfnl_b200.so")
 
-SOURCES = ["api.cu", "reorder.cu", "conv_ffma.cu", "nonlocal_ffma.cu", "mse.cu", "metrics.cu", "video_io.cu", "conv_tc.cu", "nonlocal_tc.cu"]
+SOURCES = ["api.cu", "reorder.cu", "conv_ffma.cu", "nonlocal_ffma.cu", "mse.cu", "metrics.cu", "video_io.cu", "conv_tc.cu", "pfrb_flow.cu", "nonlocal_tc.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

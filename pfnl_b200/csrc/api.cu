@@ -22,8 +22,35 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// Host-mapped record of a bounded device-side wait that gave up (tc_ptx.cuh wait_timeout_trap): it survives the
+// trap that follows, so the error message can say which CTA waited for what.  Process-wide, portable memory.
+static int* g_fault_host = nullptr;
+int* tc_fault_buffer() {
+  static int* dev = nullptr;
+  if (!g_fault_host) {
+    // 8 ints of fault record + 256 CTAs x 8 ints of progress marks (PFNL_FLOW_DEBUG=1, pfrb_flow.cu)
+    if (cudaHostAlloc((void**)&g_fault_host, (8 + 256 * 8) * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) !=
+        cudaSuccess) {
+      cudaGetLastError();
+      g_fault_host = nullptr;
+      return nullptr;
+    }
+    memset(g_fault_host, 0, (8 + 256 * 8) * sizeof(int));
+    if (cudaHostGetDevicePointer((void**)&dev, g_fault_host, 0) != cudaSuccess) {
+      cudaGetLastError();
+      dev = nullptr;
+    }
+  }
+  return dev;
+}
+
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
-  set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  if (g_fault_host && g_fault_host[0] != 0)
+    set_error("CUDA error %d (%s) at %s:%d: %s [device wait timed out: kind %d, CTA %d, detail %d / %d]", (int)e,
+              cudaGetErrorString(e), file, line, what, g_fault_host[0] - 1, g_fault_host[1], g_fault_host[2],
+              g_fault_host[3]);
+  else
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
   return PFNL_ERR_CUDA;
 }
 
@@ -98,6 +125,8 @@ struct pfnl_handle {
   // workspace
   char* ws = nullptr;
   size_t ws_cap = 0;
+  int* flow_flags = nullptr;  // dependency counters of the PFRB dataflow kernel (zero between launches)
+  size_t flow_cap = 0;
   double* mse_partial = nullptr;
   int mse_cap = 0;
   double* metric_buf = nullptr;  // [2][F*H*W] luma planes + partial sums of pfnl_msy / pfnl_ssim_y
@@ -164,7 +193,29 @@ int check_shape(int N, int H, int W) {
   return PFNL_OK;
 }
 
+// carve + the handle-owned pieces of the tensor-core workspace
+Workspace carve_h(pfnl_handle* h, int N, int H, int W) {
+  Workspace w = carve(h->ws, h->precision, N, H, W);
+  w.tc.flow_flags = h->flow_flags;
+  w.tc.flow_fault = tc_fault_buffer();
+  return w;
+}
+
 int ensure_workspace(pfnl_handle* h, int N, int H, int W) {
+  if (h->precision != PFNL_PREC_FP32) {
+    const size_t ints = tc_flow_flag_ints(N, H, W);
+    if (ints > h->flow_cap) {
+      if (h->flow_flags) {
+        PFNL_CUDA(cudaDeviceSynchronize());
+        PFNL_CUDA(cudaFree(h->flow_flags));
+        h->flow_flags = nullptr;
+        h->flow_cap = 0;
+      }
+      PFNL_CUDA(cudaMalloc((void**)&h->flow_flags, ints * sizeof(int)));
+      PFNL_CUDA(cudaMemset(h->flow_flags, 0, ints * sizeof(int)));
+      h->flow_cap = ints;
+    }
+  }
   const size_t need = carve(nullptr, h->precision, N, H, W).bytes;
   if (need <= h->ws_cap) return PFNL_OK;
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
@@ -249,7 +300,7 @@ int pfrb_fp32(pfnl_handle* h, int i, const float* in, float* out, Workspace& w, 
 }
 
 int forward_launches(pfnl_handle* h, const float* lr, int N, int H, int W, float* sr, cudaStream_t s) {
-  Workspace w = carve(h->ws, h->precision, N, H, W);
+  Workspace w = carve_h(h, N, H, W);
   const int L = (H / 2) * (W / 2);
   const long long hw = (long long)H * W;
   int rc;
@@ -460,6 +511,7 @@ int pfnl_destroy(pfnl_handle* h) {
   tc_destroy(h->tcw);
   for (void* p : h->allocs) cudaFree(p);
   if (h->ws) cudaFree(h->ws);
+  if (h->flow_flags) cudaFree(h->flow_flags);
   if (h->mse_partial) cudaFree(h->mse_partial);
   if (h->metric_buf) cudaFree(h->metric_buf);
   if (h->pack_scratch) cudaFree(h->pack_scratch);
@@ -495,6 +547,34 @@ int pfnl_set_graphs(pfnl_handle* h, int enable) {
     return PFNL_ERR_BAD_ARG;
   }
   h->graphs = enable != 0;
+  return PFNL_OK;
+}
+
+int pfnl_set_flow(pfnl_handle* h, int enable) {
+  if (!h) {
+    set_error("pfnl_set_flow: NULL handle");
+    return PFNL_ERR_BAD_ARG;
+  }
+  if ((enable != 0) != h->tcw.flow) {  // captured graphs hold the other launch sequence
+    DeviceGuard guard(h->device);
+    PFNL_CUDA(cudaDeviceSynchronize());
+    for (auto& kv : h->graph_cache) cudaGraphExecDestroy(kv.second);
+    h->graph_cache.clear();
+    h->graph_nodes.clear();
+  }
+  h->tcw.flow = enable != 0;
+  return PFNL_OK;
+}
+
+int pfnl_debug_fault(int* out4) {
+  if (!out4) return PFNL_ERR_BAD_ARG;
+  for (int i = 0; i < 4; ++i) out4[i] = g_fault_host ? g_fault_host[i] : 0;
+  return PFNL_OK;
+}
+
+int pfnl_debug_progress(int* out, int n) {
+  if (!out || n < 0 || n > 256 * 8) return PFNL_ERR_BAD_ARG;
+  for (int i = 0; i < n; ++i) out[i] = g_fault_host ? g_fault_host[8 + i] : 0;
   return PFNL_OK;
 }
 
@@ -548,7 +628,8 @@ int pfnl_forward(pfnl_handle* h, const float* lr, int N, int H, int W, float* sr
   PFNL_CUDA(cudaStreamIsCapturing(s, &cap));
   if (cap == cudaStreamCaptureStatusNone) {
     if ((rc = ensure_workspace(h, N, H, W))) return rc;
-  } else if (carve(nullptr, h->precision, N, H, W).bytes > h->ws_cap) {
+  } else if (carve(nullptr, h->precision, N, H, W).bytes > h->ws_cap ||
+             (h->precision != PFNL_PREC_FP32 && tc_flow_flag_ints(N, H, W) > h->flow_cap)) {
     set_error("pfnl_forward: stream is capturing and the workspace for (%d,%d,%d) is not reserved", N, H, W);
     return PFNL_ERR_BAD_ARG;
   }
@@ -812,10 +893,62 @@ int pfnl_pfrb(pfnl_handle* h, int blk, const float* frames, int N, int H, int W,
   if (rc) return rc;
   DeviceGuard guard(h->device);
   if ((rc = ensure_workspace(h, N, H, W))) return rc;
-  Workspace w = carve(h->ws, h->precision, N, H, W);
+  Workspace w = carve_h(h, N, H, W);
   cudaStream_t s = (cudaStream_t)stream;
   if (h->precision == PFNL_PREC_FP32) return pfrb_fp32(h, blk, frames, frames_out, w, N, H, W, s);
   return tc_pfrb_fp32io(h->tcw, w.tc, h->precision, blk, frames, N, H, W, frames_out, s, &h->launches);
+}
+
+int pfnl_conv0(pfnl_handle* h, const float* inp21, int N, int H, int W, float* frames_out, void* stream) {
+  if (!h || !inp21 || !frames_out) {
+    set_error("pfnl_conv0: NULL argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  int rc = check_shape(N, H, W);
+  if (rc) return rc;
+  DeviceGuard guard(h->device);
+  if ((rc = ensure_workspace(h, N, H, W))) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->precision == PFNL_PREC_FP32) {
+    if ((rc = launch_conv0(inp21, N, H, W, h->conv0_w, h->conv0_b, frames_out, s))) return rc;
+    h->launches += 1;
+    return PFNL_OK;
+  }
+  Workspace w = carve_h(h, N, H, W);
+  return tc_conv0_fp32io(h->tcw, w.tc, h->precision, inp21, N, H, W, frames_out, s, &h->launches);
+}
+
+int pfnl_convmerge1(pfnl_handle* h, const float* frames, int N, int H, int W, float* merge, void* stream) {
+  if (!h || !frames || !merge) {
+    set_error("pfnl_convmerge1: NULL argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  int rc = check_shape(N, H, W);
+  if (rc) return rc;
+  DeviceGuard guard(h->device);
+  if ((rc = ensure_workspace(h, N, H, W))) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->precision == PFNL_PREC_FP32) {
+    const long long hw = (long long)H * W;
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.H = H;
+    a.W = W;
+    a.act = 1;
+    a.cout = 48;
+    a.nslices = kFrames;
+    a.slice_ch = kMF;
+    for (int t = 0; t < kFrames; ++t) a.slice[t] = make_slice(frames + t * hw * kMF, kFrames * hw * kMF, 1, kMF);
+    a.images = N;
+    a.wpack = h->merge1_p;
+    a.bias = h->merge1_b;
+    a.out = merge;
+    if ((rc = launch_conv_ffma(3, a, s))) return rc;
+    h->launches += 1;
+    return PFNL_OK;
+  }
+  Workspace w = carve_h(h, N, H, W);
+  return tc_merge1_fp32io(h->tcw, w.tc, h->precision, frames, N, H, W, merge, s, &h->launches);
 }
 
 int pfnl_downsample4(pfnl_handle* h, const float* hr, int F, int H, int W, const float* blur_host, float* lr,

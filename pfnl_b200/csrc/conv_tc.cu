@@ -43,24 +43,9 @@
 // leaky_relu / partial sums / residual -> fp16 planes (16-byte accesses, 4 full lines per warp
 // instruction) or fp32, operands prefetched before the accumulator wait).  TMEM accumulators are double buffered.  Programmatic
 // dependent launch overlaps the prologue with the previous kernel's tail.
-#include <cuda_fp16.h>
-
-#include "common.cuh"
-#include "kernels.h"
-#include "tc.h"
-#include "tc_ptx.cuh"
-#include "tc_tmap.h"
+#include "conv_tc_dev.cuh"
 
 namespace pfnl {
-
-using namespace tc;
-
-enum TcEpi {
-  kEpiActPlanes = 0,   // v = lrelu(acc + bias)                        -> fp16 planes
-  kEpiPartialF32 = 1,  // v = acc (+ previous content if accumulate)   -> fp32
-  kEpiResPlanes = 2,   // v = lrelu(acc + pbase + bias) + residual     -> fp16 planes (may alias residual)
-  kEpiFinalF32 = 3     // v = lrelu(acc + previous + bias)             -> fp32
-};
 
 struct TcPhase {
   CUtensorMap tm_hi, tm_lo;  // source planes
@@ -96,19 +81,6 @@ struct TcCommon {
     if (cm.trace != nullptr && blockIdx.x == 0 && (ev) < 64) cm.trace[(role) * 64 + (ev)] = clock64(); \
   } while (0)
 
-// compile-time description of one phase
-template <int KS_, int NSRC_, int NOUT_, int NCH_>
-struct PhaseCfg {
-  static constexpr int KS = KS_, NSRC = NSRC_, NOUT = NOUT_, NCH = NCH_;
-  static constexpr int TAPS = KS * KS;
-  static constexpr int NTAPS = NSRC * TAPS;
-  static constexpr int BOX_W = KS == 3 ? kTcPatchW3 : 8;
-  static constexpr int BOX_H = KS == 3 ? 18 : 16;
-  static constexpr int PATCH_BYTES = BOX_W * BOX_H * 128;
-  static constexpr int WT_BYTES = NOUT * 128;  // one plane of one tap: [NOUT rows][64 ci]
-};
-
-constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
 template <class P0, class P1, int NSPLIT>
 struct KernelCfg {
@@ -134,105 +106,18 @@ struct KernelCfg {
 
 constexpr int kPrefetchAhead = 0;                   // tiles of L2 prefetch distance in the TMA producer (0 = off: the
                                                     // prefetches occupy the same TMA engine as the loads they hide)
-constexpr int kTcEpiWarps = 16;                     // 4 TMEM lane quarters x 4 sixteen-channel chunks
-constexpr int kTcThreads = (2 + kTcEpiWarps) * 32;  // + producer warp + MMA warp = 576
 
 struct TcCtrl {
   uint64_t wfull;        // weight image of the current phase has landed
   uint64_t wfree;        // all MMAs of the finished phase are complete (weights may be overwritten)
   uint64_t stores_done;  // all epilogue stores of the finished phase are globally visible
-  uint64_t full[8], empty[8];
-  uint64_t tmem_full[2], tmem_empty[2];
+  TcBars bars;
   uint32_t tmem_base;
   float bias[kTcMaxPhases][64];
 };
 
-struct TcRing {  // ring slot cursor (producer and MMA issuer keep identical copies)
-  int sl, ph;
-};
-
-__device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
-  hi = __float2half_rn(v);
-  lo = __float2half_rn((v - __half2float(hi)) * 2048.f);
-}
-
-// element offset of (image, 8-channel chunk, y, x) in a channel-chunk-major fp16 plane [img][8][H][W][8]
-__device__ __forceinline__ long long plane_off(int img, int chunk8, int y, int x, int H, int W) {
-  return ((((long long)img * 8 + chunk8) * H + y) * W + x) * 8;
-}
-// fp32 partial sums of conv2's base half: [img][4 chunks][H][W][16] (64 contiguous bytes per thread)
-__device__ __forceinline__ long long pbase_off(int img, int chunk16, int y, int x, int H, int W) {
-  return ((((long long)img * 4 + chunk16) * H + y) * W + x) * 16;
-}
-
-// accumulation chain of tap tp (3x3: taps 0-4 -> chain 0, 5-8 -> chain 1 when NCH = 2) or source s
-template <int KS, int NCH>
-__device__ __forceinline__ constexpr int tc_chain(int tp, int s) {
-  return NCH == 1 ? 0 : (KS == 3 ? (NCH == 2 ? (tp >= 5 ? 1 : 0) : tp / 3) : s % NCH);
-}
-
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per lane, half the
-// LSU requests of two 16-byte accesses for the thread-per-pixel-row pattern of the epilogue.
-struct __align__(32) U256 {
-  uint32_t w[8];
-};
-__device__ __forceinline__ U256 ld256(const void* ptr) {
-  U256 r;
-  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
-                 "=r"(r.w[7])
-               : "l"(ptr)
-               : "memory");
-  return r;
-}
-__device__ __forceinline__ void st256(void* ptr, const U256& r) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(r.w[0]), "r"(r.w[1]), "r"(r.w[2]),
-               "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]), "r"(r.w[7])
-               : "memory");
-}
-// one fp16 plane access of an epilogue thread: its 16 channels = two 16-byte pieces, `cs` elements apart
-// (cs = H*W*8, the chunk stride of the plane)
-__device__ __forceinline__ U256 ld_plane16(const __half* p, long long cs) {
-  U256 r;
-  const uint4 a = *reinterpret_cast<const uint4*>(p);
-  const uint4 b = *reinterpret_cast<const uint4*>(p + cs);
-  r.w[0] = a.x, r.w[1] = a.y, r.w[2] = a.z, r.w[3] = a.w;
-  r.w[4] = b.x, r.w[5] = b.y, r.w[6] = b.z, r.w[7] = b.w;
-  return r;
-}
-__device__ __forceinline__ void st_plane16(__half* p, long long cs, const U256& r) {
-  *reinterpret_cast<uint4*>(p) = make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]);
-  *reinterpret_cast<uint4*>(p + cs) = make_uint4(r.w[4], r.w[5], r.w[6], r.w[7]);
-}
-__device__ __forceinline__ long long globaltimer_ns() {
-  long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-// Whole weight image: linear bulk copies L2 -> smem (the image is stored pre-swizzled, UMMA-ready).
-template <int W_BYTES>
-__device__ __forceinline__ void load_weights(uint8_t* wsm, const __half* wimg, uint64_t* wfull) {
-  for (int off = 0; off < W_BYTES; off += 32768) {
-    const int n = (W_BYTES - off) < 32768 ? (W_BYTES - off) : 32768;
-    bulk_load(wsm + off, reinterpret_cast<const uint8_t*>(wimg) + off, n, wfull);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------
-// role bodies, one call per phase
+// role bodies, one call per phase (the per-tile bodies live in conv_tc_dev.cuh)
 // ---------------------------------------------------------------------------------------------------------
 // Issues the patch loads of tiles [first, first + count) of this CTA's tile sequence in phase P (count < 0:
 // all remaining).  The first tile of a phase whose inputs do not depend on the previous phase is issued
@@ -252,39 +137,8 @@ __device__ __forceinline__ void producer_phase(const TcPhase& P, const TcCommon&
       const int r = u / cm.tiles_x;
       const int ty = r % cm.tiles_y;
       const int img = (r / cm.tiles_y) * P.frames + t;
-      const int x0 = tx * 8 - PAD, y0 = ty * 16 - PAD;
-      if (kPrefetchAhead > 0) {  // L2 prefetch kPrefetchAhead tiles ahead
-        int ft = t + kPrefetchAhead, fu = u;
-        while (ft >= P.frames) {
-          ft -= P.frames;
-          fu += gridDim.x;
-        }
-        if (fu < P.n_units) {
-          const int ftx = fu % cm.tiles_x;
-          const int fr = fu / cm.tiles_x;
-          const int fty = fr % cm.tiles_y;
-          const int fimg = (fr / cm.tiles_y) * P.frames + ft;
-          for (int s = 0; s < PC::NSRC; ++s) {
-            const int fic = fimg * P.img_mul + P.img_add + s;
-            tma_prefetch_4d(&P.tm_hi, (ftx * 8 - PAD) * 8, fty * 16 - PAD, 0, fic);
-            if (NSPLIT == 2) tma_prefetch_4d(&P.tm_lo, (ftx * 8 - PAD) * 8, fty * 16 - PAD, 0, fic);
-          }
-        }
-      }
-      for (int s = 0; s < PC::NSRC; ++s) {
-        const int ic = img * P.img_mul + P.img_add + s;
-#pragma unroll
-        for (int pl = 0; pl < NSPLIT; ++pl) {  // hi plane first (consumed first), then lo
-          mbar_wait(&ctl->empty[rg.sl], rg.ph ^ 1);
-          mbar_arrive_expect_tx(&ctl->full[rg.sl], PC::PATCH_BYTES);
-          tma_load_4d(ring + rg.sl * KC::SLOT_BYTES, pl == 1 ? &P.tm_lo : &P.tm_hi, &ctl->full[rg.sl], x0 * 8, y0, 0,
-                      ic);
-          if (++rg.sl == KC::NS) {
-            rg.sl = 0;
-            rg.ph ^= 1;
-          }
-        }
-      }
+      load_tile<PC, NSPLIT, KC::NS, KC::SLOT_BYTES>(&P.tm_hi, &P.tm_lo, ring, &ctl->bars, rg, tx * 8 - PAD,
+                                                    ty * 16 - PAD, img * P.img_mul + P.img_add);
       TC_TRACE(0, tcount);
     }
 }
@@ -292,215 +146,42 @@ __device__ __forceinline__ void producer_phase(const TcPhase& P, const TcCommon&
 template <class PC, class KC, int NSPLIT>
 __device__ __forceinline__ void mma_phase(const TcPhase& P, const TcCommon& cm, uint8_t* wsm, uint8_t* ring,
                                           TcCtrl* ctl, uint32_t tmem, TcRing& rg, int& it, int lane) {
-  constexpr int KS = PC::KS, NSRC = PC::NSRC, NOUT = PC::NOUT, NCH = PC::NCH, TAPS = PC::TAPS;
-  constexpr int TAP_BYTES = NSPLIT * PC::WT_BYTES;
-  constexpr uint32_t idesc_lo = make_idesc_f16(128, NOUT);           // A_lo x W_hi          -> D1
-  constexpr uint32_t idesc_hi = make_idesc_f16(128, NSPLIT * NOUT);  // A_hi x [W_hi ; W_lo] -> [D0 | D1]
-  // A operand (un-swizzled K-major): pixels of 16 B per 8-channel sub-patch; an 8-pixel tile row is one core
-  // matrix, consecutive tile rows are one patch row apart (SBO), the two k-chunks one sub-patch apart (LBO)
-  constexpr uint32_t SBO_A = PC::BOX_W * 16;
-  constexpr uint32_t SUB_A = PC::BOX_W * PC::BOX_H * 16;  // bytes per sub-patch
-  const uint64_t wd = make_sdesc_sw128(smem_u32(wsm), 1024, 0);
+  long long* tr = (cm.trace != nullptr && blockIdx.x == 0) ? cm.trace : nullptr;
   for (int u = blockIdx.x; u < P.n_units; u += gridDim.x)
-    for (int t = 0; t < P.frames; ++t, ++it) {
-      const int buf = it & 1;
-      mbar_wait(&ctl->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
-      fence_after_sync();
-      const uint32_t dbase = tmem + buf * KC::TMEM_BUF_COLS;
-      uint32_t accmask = 0;  // bit c: chain c's block [D0|D1] has been written in this tile
-      for (int s = 0; s < NSRC; ++s) {
-        const uint64_t wsd = wd + (uint64_t)((s * TAPS * TAP_BYTES) >> 4);
-        // ---- hi-plane pass: [D0_c | D1_c] (+)= A_hi x [W_hi ; W_lo]
-        mbar_wait(&ctl->full[rg.sl], rg.ph);
-        fence_after_sync();
-        if (lane == 0 && s == 0) TC_TRACE(1, 1 + 2 * it);
-        {
-          const uint64_t ad = make_sdesc_interleave(smem_u32(ring + rg.sl * KC::SLOT_BYTES), SUB_A, SBO_A);
-          if (elect_one()) {
-            uint32_t am = accmask;
-#pragma unroll
-            for (int tp = 0; tp < TAPS; ++tp) {
-              const int ch = tc_chain<KS, NCH>(tp, s);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint32_t aoff = (((tp / KS) * PC::BOX_W + (tp % KS)) * 16 + k * 2 * SUB_A) >> 4;
-                const uint32_t boff = (tp * TAP_BYTES + k * 32) >> 4;
-                mma_f16(dbase + ch * KC::CH_STRIDE, ad + aoff, wsd + boff, idesc_hi, (am >> ch) & 1u);
-                am |= 1u << ch;
-              }
-            }
-            mma_commit(&ctl->empty[rg.sl]);
-            if (NSPLIT == 1 && s == NSRC - 1) mma_commit(&ctl->tmem_full[buf]);
-          }
-          __syncwarp();
-#pragma unroll
-          for (int tp = 0; tp < TAPS; ++tp) accmask |= 1u << tc_chain<KS, NCH>(tp, s);
-          if (++rg.sl == KC::NS) {
-            rg.sl = 0;
-            rg.ph ^= 1;
-          }
-        }
-        if (NSPLIT == 2) {
-          // ---- lo-plane pass: D1 of chain 0 += A_lo x W_hi (chain 0 was initialised by the hi pass:
-          //      tap 0 / source 0 always belongs to chain 0), so this always accumulates
-          mbar_wait(&ctl->full[rg.sl], rg.ph);
-          fence_after_sync();
-          const uint64_t ad = make_sdesc_interleave(smem_u32(ring + rg.sl * KC::SLOT_BYTES), SUB_A, SBO_A);
-          if (elect_one()) {
-#pragma unroll
-            for (int tp = 0; tp < TAPS; ++tp) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint32_t aoff = (((tp / KS) * PC::BOX_W + (tp % KS)) * 16 + k * 2 * SUB_A) >> 4;
-                const uint32_t boff = (tp * TAP_BYTES + k * 32) >> 4;
-                mma_f16(dbase + NOUT, ad + aoff, wsd + boff, idesc_lo, 1u);
-              }
-            }
-            mma_commit(&ctl->empty[rg.sl]);
-            if (s == NSRC - 1) mma_commit(&ctl->tmem_full[buf]);  // same thread that issued the MMAs
-          }
-          __syncwarp();
-          if (++rg.sl == KC::NS) {
-            rg.sl = 0;
-            rg.ph ^= 1;
-          }
-        }
-        if (lane == 0 && s == NSRC - 1) TC_TRACE(1, 2 + 2 * it);
-      }
-    }
+    for (int t = 0; t < P.frames; ++t, ++it)
+      mma_tile<PC, NSPLIT, KC::NS, KC::SLOT_BYTES, KC::TMEM_BUF_COLS, KC::CH_STRIDE>(wsm, ring, &ctl->bars, tmem, rg, it,
+                                                                                  lane, tr);
 }
 
 template <class PC, class KC, int NSPLIT>
 __device__ __forceinline__ void epilogue_phase(const TcPhase& P, const TcCommon& cm, TcCtrl* ctl, const float* bias_sm,
                                                uint32_t tmem, int& it, int warp, int lane) {
-  constexpr int NOUT = PC::NOUT, NCH = PC::NCH;
-  const int q = warp & 3;             // TMEM lane quarter this warp may access (hardware restriction)
-  const int c0 = ((warp - 2) >> 2) * 16;
-  const bool chunk_active = c0 < NOUT;
-  const int m = q * 32 + lane;        // row of the tile = TMEM lane
-  const int my = m >> 3, mx = m & 7;  // pixel inside the 16x8 tile
-  const bool epi_planes = P.epi == kEpiActPlanes || P.epi == kEpiResPlanes;
-  const bool epi_res = P.epi == kEpiResPlanes;
-  const bool epi_prev = (P.epi == kEpiPartialF32 && P.accumulate) || P.epi == kEpiFinalF32;
+  long long* tr = (cm.trace != nullptr && blockIdx.x == 0) ? cm.trace : nullptr;
+  TcEpiArgs E;
+  E.epi = P.epi;
+  E.accumulate = P.accumulate;
+  E.f32_chunked = P.f32_chunked;
+  E.coherent_pbase = 0;  // written by the same threads in the previous phase
+  E.pbase = P.pbase;
+  E.out_hi = P.out_hi;
+  E.out_lo = P.out_lo;
+  E.res_hi = P.res_hi;
+  E.res_lo = P.res_lo;
+  E.out_f32 = P.out_f32;
+  E.H = cm.H;
+  E.W = cm.W;
   U256 pre[2];  // 16 fp32: partial sums (kept across the unit's frames) or previous fp32 content
 #pragma unroll
   for (int j = 0; j < 8; ++j) pre[0].w[j] = pre[1].w[j] = 0u;
+  TcNoHook nohook;
   for (int u = blockIdx.x; u < P.n_units; u += gridDim.x)
     for (int t = 0; t < P.frames; ++t, ++it) {
-      const int buf = it & 1;
       const int tx = u % cm.tiles_x;
       const int r = u / cm.tiles_x;
       const int ty = r % cm.tiles_y;
       const int nimg = r / cm.tiles_y;
-      const int img = nimg * P.frames + t;
-      const int y = ty * 16 + my, x = tx * 8 + mx;
-      const bool inb = chunk_active && y < cm.H && x < cm.W;
-      const long long pix = ((long long)img * cm.H + y) * cm.W + x;
-      const long long poff = plane_off(img, c0 >> 3, y, x, cm.H, cm.W);  // this thread's first 8 channels in a plane
-      const long long cs = (long long)cm.H * cm.W * 8;                    // ... the other 8 are one chunk further
-      const long long foff = pbase_off(img, c0 >> 4, y, x, cm.H, cm.W);
-      // ---- prefetch (independent of the accumulator) ----
-      U256 rh, rl;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) rh.w[j] = rl.w[j] = 0u;
-      if (inb) {
-        if (epi_res) {
-          if (t == 0) {  // the base-half partial sums are shared by the unit's 7 frames: load once
-            const float* pb = P.pbase + pbase_off(nimg, c0 >> 4, y, x, cm.H, cm.W);
-            pre[0] = ld256(pb);
-            pre[1] = ld256(pb + 8);
-          }
-          rh = ld_plane16(P.res_hi + poff, cs);
-          if (NSPLIT == 2) rl = ld_plane16(P.res_lo + poff, cs);
-        } else if (epi_prev) {
-          const float* o = P.out_f32 + (P.f32_chunked ? foff : pix * NOUT + c0);
-          pre[0] = ld256(o);
-          pre[1] = ld256(o + 8);
-        }
-      }
-      mbar_wait(&ctl->tmem_full[buf], (it >> 1) & 1);
-      fence_after_sync();
-      if (warp == 2 && lane == 0) TC_TRACE(2, 2 * it);
-      float v[16];
-      if (chunk_active) {
-        // chain c: D0 at c*CH_STRIDE, D1 (split mode) at c*CH_STRIDE + NOUT.  Chains are summed in
-        // fp32 round-to-nearest here; D1 carries the 2^-11-scaled cross terms.
-        const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + buf * KC::TMEM_BUF_COLS + c0;
-        uint32_t d0[NCH][16], d1[NSPLIT == 2 ? NCH : 1][16];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          tmem_ld_32x32b_x16(t0 + c * KC::CH_STRIDE, d0[c]);
-          if (NSPLIT == 2) tmem_ld_32x32b_x16(t0 + c * KC::CH_STRIDE + NOUT, d1[c]);
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float a = __uint_as_float(d0[0][j]);
-#pragma unroll
-          for (int c = 1; c < NCH; ++c) a += __uint_as_float(d0[c][j]);
-          if (NSPLIT == 2) {
-            float b = __uint_as_float(d1[0][j]);
-#pragma unroll
-            for (int c = 1; c < NCH; ++c) b += __uint_as_float(d1[c][j]);
-            a = fmaf(b, 1.f / 2048.f, a);
-          }
-          v[j] = a;
-        }
-      }
-      // this warp's tcgen05.ld are complete: hand the TMEM buffer back before the global stores
-      fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ctl->tmem_empty[buf]);
-      if (inb) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {  // + partial sums / previous content (zeros otherwise)
-          v[j] += __uint_as_float(pre[0].w[j]);
-          v[8 + j] += __uint_as_float(pre[1].w[j]);
-        }
-        if (epi_planes) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = lrelu(v[j] + bias_sm[c0 + j]);
-          if (epi_res) {
-            const __half* hh = reinterpret_cast<const __half*>(&rh);
-            if (NSPLIT == 2) {
-              // residual = hi + lo/2048 (exactly representable in fp32), then one rounded add
-              const __half* hl = reinterpret_cast<const __half*>(&rl);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] += fmaf(__half2float(hl[j]), 1.f / 2048.f, __half2float(hh[j]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] += __half2float(hh[j]);
-            }
-          }
-          U256 oh, ol;
-          __half* ph = reinterpret_cast<__half*>(&oh);
-          __half* pl = reinterpret_cast<__half*>(&ol);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (NSPLIT == 2)
-              split_half(v[j], ph[j], pl[j]);
-            else
-              ph[j] = __float2half_rn(v[j]);
-          }
-          st_plane16(P.out_hi + poff, cs, oh);
-          if (NSPLIT == 2) st_plane16(P.out_lo + poff, cs, ol);
-        } else {
-          if (P.epi == kEpiFinalF32) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = lrelu(v[j] + bias_sm[c0 + j]);
-          }
-          U256 o0, o1;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            o0.w[j] = __float_as_uint(v[j]);
-            o1.w[j] = __float_as_uint(v[8 + j]);
-          }
-          float* o = P.out_f32 + (P.f32_chunked ? foff : pix * NOUT + c0);
-          st256(o, o0);
-          st256(o + 8, o1);
-        }
-      }
-      if (warp == 2 && lane == 0) TC_TRACE(2, 2 * it + 1);
+      epi_tile<PC, NSPLIT, KC::TMEM_BUF_COLS, KC::CH_STRIDE>(E, &ctl->bars, bias_sm, tmem, it, warp, lane,
+                                                             nimg * P.frames + t, nimg, tx, ty, t == 0, pre, tr, nohook);
     }
 }
 
@@ -526,12 +207,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     mbar_init(&ctl->wfree, 1);
     mbar_init(&ctl->stores_done, kTcEpiWarps);
     for (int i = 0; i < 8; ++i) {
-      mbar_init(&ctl->full[i], 1);
-      mbar_init(&ctl->empty[i], 1);
+      mbar_init(&ctl->bars.full[i], 1);
+      mbar_init(&ctl->bars.empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&ctl->tmem_full[i], 1);
-      mbar_init(&ctl->tmem_empty[i], kTcEpiWarps);
+      mbar_init(&ctl->bars.tmem_full[i], 1);
+      mbar_init(&ctl->bars.tmem_empty[i], kTcEpiWarps);
     }
     fence_mbar_init();
     fence_proxy_async();
@@ -967,7 +648,6 @@ __global__ void __launch_bounds__(128) conv0_tc_kernel(const float* __restrict__
 // ---- host side --------------------------------------------------------------------------------------------
 namespace {
 
-int g_num_sms = 0;
 bool g_pdl = true;
 
 bool pdl_enabled() {
@@ -989,7 +669,8 @@ int phase_sources(TcPhase& ph, const void* src_hi, const void* src_lo, int src_i
 
 // Launches one persistent kernel running phase a and (optionally) phase b on the same units.
 template <class P0, class P1, int NSPLIT>
-int launch_tc(const TcProgram& prog, int nphases, bool phase1_reads_phase0, int H, int W, cudaStream_t s) {
+int launch_tc(const TcProgram& prog, int nphases, bool phase1_reads_phase0, int H, int W, int num_sms,
+              cudaStream_t s) {
   const TcPhase& a = prog.ph[0];
   using KC = KernelCfg<P0, P1, NSPLIT>;
   TcCommon cm;
@@ -1006,7 +687,7 @@ int launch_tc(const TcProgram& prog, int nphases, bool phase1_reads_phase0, int 
       set_error("launch_tc: phases must cover the same work units (%d vs %d)", a.n_units, prog.ph[i].n_units);
       return PFNL_ERR_BAD_ARG;
     }
-  int grid = a.n_units < g_num_sms ? a.n_units : g_num_sms;
+  int grid = a.n_units < num_sms ? a.n_units : num_sms;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
@@ -1110,16 +791,19 @@ int pack_weights(const float* hwio, int taps, int cin_total, int ci_off, int cou
 void tc_carve(TcWorkspace& w, int precision, int N, int H, int W, const std::function<char*(size_t)>& take) {
   const int nsplit = tc_nsplit(precision);
   for (int pl = 0; pl < 2; ++pl) {
-    w.actA[pl] = w.actB[pl] = w.base[pl] = nullptr;
+    w.actA[pl] = w.actA2[pl] = w.actB[pl] = w.base[pl] = nullptr;
   }
   for (int pl = 0; pl < nsplit; ++pl) {
     w.actA[pl] = take(plane_bytes(N * kFrames, H, W));
+    w.actA2[pl] = take(plane_bytes(N * kFrames, H, W));
     w.actB[pl] = take(plane_bytes(N * kFrames, H, W));
     w.base[pl] = take(plane_bytes(N, H, W));
   }
   w.pbase = (float*)take((size_t)N * H * W * 64 * sizeof(float));
   w.nl_x16 = nullptr;
   w.nl_priv = nullptr;
+  w.flow_flags = nullptr;
+  w.flow_fault = nullptr;
   if (tc_nl_on_tensor_cores(precision) && tc_has_nonlocal()) {
     const int L = (H / 2) * (W / 2);
     w.nl_x16 = take(tc_nl_workspace_bytes(N, L));
@@ -1136,7 +820,8 @@ int tc_init(TcWeights& tw, int precision, const TcRawWeights& raw, std::vector<v
   int dev = 0;
   PFNL_CUDA(cudaGetDevice(&dev));
   PFNL_CUDA(cudaGetDeviceProperties(&prop, dev));
-  g_num_sms = prop.multiProcessorCount;
+  tw.num_sms = prop.multiProcessorCount;
+  tw.flow = tc_flow_default();
   tw.precision = precision;
   tw.nsplit = tc_nsplit(precision);
   tw.raw = raw;
@@ -1148,6 +833,7 @@ int tc_init(TcWeights& tw, int precision, const TcRawWeights& raw, std::vector<v
   if ((rc = set_attr<Shapes<2>::C3, Shapes<2>::C3, 2>())) return rc;
   if ((rc = set_attr<Shapes<2>::CM, Shapes<2>::CM, 2>())) return rc;
   if ((rc = tc_nl_init())) return rc;
+  if ((rc = tc_flow_init())) return rc;
   PFNL_CUDA(cudaFuncSetAttribute(conv0_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv0Cfg<1>::SMEM));
   PFNL_CUDA(cudaFuncSetAttribute(conv0_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv0Cfg<2>::SMEM));
   const int ns = tw.nsplit;
@@ -1234,7 +920,7 @@ int pfrb_tc(const TcWeights& tw, TcWorkspace& w, int i, int N, int H, int W, cud
   b.out_hi = (__half*)w.base[0];
   b.out_lo = (__half*)w.base[1];
   if (prof) prof->begin(kProfConv1, s);
-  rc = launch_tc<typename SH::C3, typename SH::C10, NSPLIT>(prog, 2, true, H, W, s);
+  rc = launch_tc<typename SH::C3, typename SH::C10, NSPLIT>(prog, 2, true, H, W, tw.num_sms, s);
   if (prof) prof->end(s);
   if (rc) return rc;
   // ---- launch B: conv2_i(concat[base, inp1[t]]) = conv(base; W2[:,:,0:64]) + conv(inp1[t]; W2[:,:,64:128]):
@@ -1263,19 +949,16 @@ int pfrb_tc(const TcWeights& tw, TcWorkspace& w, int i, int N, int H, int W, cud
   b.out_hi = (__half*)w.actA[0];
   b.out_lo = (__half*)w.actA[1];
   if (prof) prof->begin(kProfConv2, s);
-  rc = launch_tc<typename SH::C3, typename SH::C3, NSPLIT>(prog, 2, false, H, W, s);
+  rc = launch_tc<typename SH::C3, typename SH::C3, NSPLIT>(prog, 2, false, H, W, tw.num_sms, s);
   if (prof) prof->end(s);
   if (rc) return rc;
   *launches += 2;
   return PFNL_OK;
 }
 
+// conv0 on each frame (model/pfnl.py:61-62): inp21 [N,H,W,21] fp32 -> fp16 planes of inp0 (actA)
 template <int NSPLIT>
-int trunk_tc(const TcWeights& tw, TcWorkspace& w, const float* inp21, int N, int H, int W, float* merge,
-             cudaStream_t s, long long* launches, Profiler* prof) {
-  using SH = Shapes<NSPLIT>;
-  int rc;
-  if (prof) prof->begin(kProfConv0, s);
+int conv0_tc(const TcWeights& tw, TcWorkspace& w, const float* inp21, int N, int H, int W, cudaStream_t s) {
   static const bool conv0_ffma = getenv("PFNL_TC_CONV0_FFMA") != nullptr;  // the CUDA-core version, kept for A/B runs
   if (conv0_ffma) {
     dim3 grid(ceil_div(W, 16) * ceil_div(H, 16), N * kFrames);
@@ -1286,7 +969,7 @@ int trunk_tc(const TcWeights& tw, TcWorkspace& w, const float* inp21, int N, int
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     const int ntiles = tiles_x * tiles_y * N * kFrames;
-    cfg.gridDim = dim3(ntiles < 3 * g_num_sms ? ntiles : 3 * g_num_sms);  // 3 CTAs per SM, each keeps its weights
+    cfg.gridDim = dim3(ntiles < 3 * tw.num_sms ? ntiles : 3 * tw.num_sms);  // 3 CTAs per SM, each keeps its weights
     cfg.blockDim = dim3(128);
     cfg.dynamicSmemBytes = Conv0Cfg<NSPLIT>::SMEM;
     cfg.stream = s;
@@ -1302,13 +985,16 @@ int trunk_tc(const TcWeights& tw, TcWorkspace& w, const float* inp21, int N, int
     PFNL_CUDA(cudaLaunchKernelEx(&cfg, conv0_tc_kernel<NSPLIT>, inp21, H, W, tiles_x, tiles_y, ntiles,
                                  (const __half*)tw.conv0, tw.raw.conv0_b, (__half*)w.actA[0], (__half*)w.actA[1]));
   }
-  if (prof) prof->end(s);
   PFNL_LAUNCH_CHECK();
-  *launches += 1;
-  for (int i = 0; i < PFNL_NUM_BLOCK; ++i)
-    if ((rc = pfrb_tc<NSPLIT>(tw, w, i, N, H, W, s, launches, prof))) return rc;
-  // merge = convmerge1(concat_t inp0[t])                          pfnl.py:73-74: ONE launch, 7 phases - frame slice t
-  // of the K = 7*576 contraction per phase, fp32 partial sums accumulated in place by the same threads
+  return PFNL_OK;
+}
+
+// merge = convmerge1(concat_t inp0[t])  (model/pfnl.py:73-74) from the fp16 planes in actA: ONE launch, 7 phases -
+// frame slice t of the K = 7*576 contraction per phase, fp32 partial sums accumulated in place by the same threads
+template <int NSPLIT>
+int merge1_tc(const TcWeights& tw, TcWorkspace& w, int N, int H, int W, float* merge, cudaStream_t s) {
+  using SH = Shapes<NSPLIT>;
+  int rc;
   const int units = N * ceil_div(W, 8) * ceil_div(H, 16);
   const size_t per = (size_t)NSPLIT * 9 * 48 * 128;
   TcProgram prog;
@@ -1326,8 +1012,31 @@ int trunk_tc(const TcWeights& tw, TcWorkspace& w, const float* inp21, int N, int
     a.bias = t == kFrames - 1 ? tw.raw.merge1_b : nullptr;
     a.out_f32 = merge;
   }
+  return launch_tc<typename SH::CM, typename SH::CM, NSPLIT>(prog, kFrames, false, H, W, tw.num_sms, s);
+}
+
+template <int NSPLIT>
+int trunk_tc(const TcWeights& tw, TcWorkspace& w, const float* inp21, int N, int H, int W, float* merge,
+             cudaStream_t s, long long* launches, Profiler* prof) {
+  int rc;
+  if (prof) prof->begin(kProfConv0, s);
+  rc = conv0_tc<NSPLIT>(tw, w, inp21, N, H, W, s);
+  if (prof) prof->end(s);
+  if (rc) return rc;
+  *launches += 1;
+  if (tw.flow) {
+    // the 20 blocks as one persistent dataflow kernel; 20 is even, so the result is back in actA
+    if (prof) prof->begin(kProfPfrbFlow, s);
+    rc = tc_pfrb_flow(tw, w, 0, PFNL_NUM_BLOCK, 0, N, H, W, pdl_enabled(), s);
+    if (prof) prof->end(s);
+    if (rc) return rc;
+    *launches += 1;
+  } else {
+    for (int i = 0; i < PFNL_NUM_BLOCK; ++i)
+      if ((rc = pfrb_tc<NSPLIT>(tw, w, i, N, H, W, s, launches, prof))) return rc;
+  }
   if (prof) prof->begin(kProfMerge1, s);
-  rc = launch_tc<typename SH::CM, typename SH::CM, NSPLIT>(prog, kFrames, false, H, W, s);
+  rc = merge1_tc<NSPLIT>(tw, w, N, H, W, merge, s);
   if (prof) prof->end(s);
   if (rc) return rc;
   *launches += 1;
@@ -1349,12 +1058,48 @@ int tc_pfrb_fp32io(const TcWeights& tw, TcWorkspace& w, int precision, int blk, 
   f32_to_planes_kernel<<<148 * 8, 256, 0, s>>>(frames, n, (long long)H * W, ns, (__half*)w.actA[0],
                                                (__half*)w.actA[1]);
   PFNL_LAUNCH_CHECK();
-  int rc = ns == 2 ? pfrb_tc<2>(tw, w, blk, N, H, W, s, launches, nullptr)
-                   : pfrb_tc<1>(tw, w, blk, N, H, W, s, launches, nullptr);
+  int rc;
+  const bool flow = tw.flow;
+  if (flow) {  // one block through the dataflow kernel: actA -> actA2
+    rc = tc_pfrb_flow(tw, w, blk, 1, 0, N, H, W, false, s);
+    *launches += 1;
+  } else {
+    rc = ns == 2 ? pfrb_tc<2>(tw, w, blk, N, H, W, s, launches, nullptr)
+                 : pfrb_tc<1>(tw, w, blk, N, H, W, s, launches, nullptr);
+  }
   if (rc) return rc;
+  planes_to_f32_kernel<<<148 * 8, 256, 0, s>>>((const __half*)(flow ? w.actA2[0] : w.actA[0]),
+                                               (const __half*)(flow ? w.actA2[1] : w.actA[1]), n, (long long)H * W,
+                                               ns, frames_out);
+  PFNL_LAUNCH_CHECK();
+  *launches += 2;
+  return PFNL_OK;
+}
+
+// Stage-level entries in the handle's precision (pfnl_conv0 / pfnl_convmerge1): the tcgen05 kernels with fp32
+// tensors either side.
+int tc_conv0_fp32io(const TcWeights& tw, TcWorkspace& w, int precision, const float* inp21, int N, int H, int W,
+                    float* frames_out, cudaStream_t s, long long* launches) {
+  const int ns = tc_nsplit(precision);
+  int rc = ns == 2 ? conv0_tc<2>(tw, w, inp21, N, H, W, s) : conv0_tc<1>(tw, w, inp21, N, H, W, s);
+  if (rc) return rc;
+  const long long n = (long long)N * kFrames * H * W * 64;
   planes_to_f32_kernel<<<148 * 8, 256, 0, s>>>((const __half*)w.actA[0], (const __half*)w.actA[1], n,
                                                (long long)H * W, ns, frames_out);
   PFNL_LAUNCH_CHECK();
+  *launches += 2;
+  return PFNL_OK;
+}
+
+int tc_merge1_fp32io(const TcWeights& tw, TcWorkspace& w, int precision, const float* frames, int N, int H, int W,
+                     float* merge, cudaStream_t s, long long* launches) {
+  const int ns = tc_nsplit(precision);
+  const long long n = (long long)N * kFrames * H * W * 64;
+  f32_to_planes_kernel<<<148 * 8, 256, 0, s>>>(frames, n, (long long)H * W, ns, (__half*)w.actA[0],
+                                               (__half*)w.actA[1]);
+  PFNL_LAUNCH_CHECK();
+  int rc = ns == 2 ? merge1_tc<2>(tw, w, N, H, W, merge, s) : merge1_tc<1>(tw, w, N, H, W, merge, s);
+  if (rc) return rc;
   *launches += 2;
   return PFNL_OK;
 }

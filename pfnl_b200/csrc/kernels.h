@@ -20,7 +20,8 @@ enum ProfKind {
   kProfMerge1 = 6,
   kProfTail = 7,
   kProfOther = 8,
-  kProfKinds = 9
+  kProfPfrbFlow = 9,  // the whole PFRB stack as one persistent dataflow kernel (pfrb_flow.cu)
+  kProfKinds = 10
 };
 struct Profiler {
   bool on = false;

@@ -20,6 +20,8 @@
 #include <cuda_fp16.h>
 #include <math.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tc.h"
@@ -144,7 +146,7 @@ template <int NSPLIT>
 __global__ void __launch_bounds__(kNlThreads, 1)
     nl_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_xl,
                  const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_gl, int L, int Lp,
-                 float* __restrict__ Y) {
+                 float* __restrict__ Y, int ksplit, float* __restrict__ Ypart, float* __restrict__ ML) {
   using CF = NlCfg<NSPLIT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -155,7 +157,12 @@ __global__ void __launch_bounds__(kNlThreads, 1)
   NlCtrl* ctl = reinterpret_cast<NlCtrl*>(p_sm + CF::PBUFS * CF::P_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = blockIdx.y, q0 = blockIdx.x * kQT;
-  const int ntiles = Lp / kKT;
+  // key split (large L, few clips): this CTA covers key tiles [j0, j0 + ntiles) of the row and writes an
+  // un-normalised partial (O, reference max, sum) that nl_merge_kernel combines (log-sum-exp merge)
+  const int split = blockIdx.z;
+  const int all_tiles = Lp / kKT;
+  const int j0 = (int)((long long)split * all_tiles / ksplit);
+  const int ntiles = (int)((long long)(split + 1) * all_tiles / ksplit) - j0;
 
   if (tid == 0) {
     mbar_init(&ctl->q_full, 1);
@@ -205,7 +212,7 @@ __global__ void __launch_bounds__(kNlThreads, 1)
 #pragma unroll
           for (int pl = 0; pl < NSPLIT; ++pl)
             tma_load_2d(k_sm + st * CF::K_BYTES + b * CF::BLK_QK + pl * CF::PLANE, pl ? &tm_xl : &tm_x,
-                        &ctl->k_full[st], b * 64, n * Lp + j * kKT);
+                        &ctl->k_full[st], b * 64, n * Lp + (j0 + j) * kKT);
         mbar_wait(&ctl->v_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&ctl->v_full[st], CF::V_BYTES);
 #pragma unroll
@@ -213,7 +220,7 @@ __global__ void __launch_bounds__(kNlThreads, 1)
 #pragma unroll
           for (int pl = 0; pl < NSPLIT; ++pl)
             tma_load_2d(v_sm + st * CF::V_BYTES + b * CF::BLK_V + pl * CF::VPLANE, pl ? &tm_gl : &tm_g,
-                        &ctl->v_full[st], j * kKT + b * 64, n * kVR);
+                        &ctl->v_full[st], (j0 + j) * kKT + b * 64, n * kVR);
       }
     }
   } else if (warp == 1) {
@@ -284,7 +291,7 @@ __global__ void __launch_bounds__(kNlThreads, 1)
       const int pb = j % CF::PBUFS;
       mbar_wait(&ctl->s_full[sb], sph);
       fence_after_sync();
-      const int kvalid = L - j * kKT - half * 64;  // keys >= kvalid of this thread's 64 are padding
+      const int kvalid = L - (j0 + j) * kKT - half * 64;  // keys >= kvalid of this thread's 64 are padding
       float mt = -INFINITY;
       uint32_t sreg[2][32];
       const uint32_t s_addr = tm_s0 + sb * CF::S_COLS + lane_addr + half * 64;
@@ -365,8 +372,14 @@ __global__ void __launch_bounds__(kNlThreads, 1)
     // l of the row = sum of the two half-row sums (both were kept against the same reference max)
     ctl->rowsum[half][row] = l_run;
     asm volatile("bar.sync 1, %0;" ::"n"(kNlSoftmaxWarps * 32) : "memory");
-    const float inv = 1.f / (l_run + ctl->rowsum[half ^ 1][row]);
+    const float l_tot = l_run + ctl->rowsum[half ^ 1][row];
+    const float inv = ksplit > 1 ? 1.f : 1.f / l_tot;  // partials stay un-normalised
     const int q = q0 + row;
+    if (ksplit > 1 && half == 0 && q < L) {
+      float* ml = ML + (((long long)split * gridDim.y + n) * L + q) * 2;
+      ml[0] = m_run;
+      ml[1] = l_tot;
+    }
     {
       uint32_t o[32];
       uint32_t o2[16];
@@ -387,7 +400,8 @@ __global__ void __launch_bounds__(kNlThreads, 1)
       }
       tmem_ld_wait();
       if (q < L) {
-        float* dst = Y + ((long long)n * L + q) * kNL + half * 48;
+        float* dst = (ksplit > 1 ? Ypart + (long long)split * gridDim.y * L * kNL : Y) +
+                     ((long long)n * L + q) * kNL + half * 48;
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
           *reinterpret_cast<float4*>(dst + i) =
@@ -405,6 +419,49 @@ __global__ void __launch_bounds__(kNlThreads, 1)
   fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// Log-sum-exp merge of the key-split partials: Y[r] = sum_s w_s O_s[r] / sum_s w_s l_s[r], w_s = exp(m_s - max_s m_s)
+// (every split saw at least one valid key, so every m_s is finite).  Thread = one row x 4 channels.
+__global__ void __launch_bounds__(256) nl_merge_kernel(const float* __restrict__ Ypart, const float* __restrict__ ML,
+                                                       int ksplit, long long rows, float* __restrict__ Y) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * (kNL / 4)) return;
+  const long long r = e / (kNL / 4);
+  const int c4 = (int)(e - r * (kNL / 4)) * 4;
+  float m = -INFINITY;
+  for (int s = 0; s < ksplit; ++s) m = fmaxf(m, ML[((long long)s * rows + r) * 2]);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float den = 0.f;
+  for (int s = 0; s < ksplit; ++s) {
+    const float w = __expf(ML[((long long)s * rows + r) * 2] - m);
+    den = fmaf(w, ML[((long long)s * rows + r) * 2 + 1], den);
+    const float4 o = *reinterpret_cast<const float4*>(Ypart + ((long long)s * rows + r) * kNL + c4);
+    acc.x = fmaf(w, o.x, acc.x);
+    acc.y = fmaf(w, o.y, acc.y);
+    acc.z = fmaf(w, o.z, acc.z);
+    acc.w = fmaf(w, o.w, acc.w);
+  }
+  const float inv = 1.f / den;
+  *reinterpret_cast<float4*>(Y + r * kNL + c4) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+}
+
+// Key splits for (N clips, L tokens) on `sms` SMs (one CTA per SM: ~210 KB of shared memory): the k <= 8 that
+// minimises waves(k)/k, each split keeping at least 2 key tiles; 1 when the query tiles alone fill the GPU or the
+// row is short (L = 256 in the headline config: 2 key tiles, latency-bound either way).
+int nl_pick_ksplit(int N, int L, int sms) {
+  const int tiles = ceil_div(L, kKT);
+  const long long base = (long long)tiles * N;
+  int best = 1;
+  double best_cost = (double)((base + sms - 1) / sms);
+  for (int k = 2; k <= 8 && k * 2 <= tiles; ++k) {
+    const double cost = (double)((base * k + sms - 1) / sms) / k + 0.01 * k;  // + a little for the merge
+    if (cost < best_cost - 1e-9) {
+      best = k;
+      best_cost = cost;
+    }
+  }
+  return best;
 }
 
 // X fp32 [N,L,84] -> X16 [plane][N,Lp,128] (zero padded; Q and K) and Xt16 [plane][N,96,Lp] = X^T (zero padded; V);
@@ -480,7 +537,7 @@ int tc_nl_init() {
 
 // `lr` != NULL: gather the tokens from the LR clip [N,7,H,W,3] (L = H/2 * W/2), `tokens` unused
 static int run_nl_tc(const float* tokens, const float* lr, int H, int W, int N, int L, int nsplit, __half* x16,
-                     __half* gt16, float* Y, cudaStream_t s) {
+                     __half* gt16, float* Y, float* part, int sms, cudaStream_t s, int* launches_out) {
   const int Lp = ceil_div(L, kKT) * kKT;
   const long long x_plane = (long long)N * Lp * kCP, g_plane = (long long)N * kVR * Lp;
   dim3 pg(Lp / 64, N);
@@ -495,18 +552,37 @@ static int run_nl_tc(const float* tokens, const float* lr, int H, int W, int N, 
     set_error("non-local tensor map encode failed (%d)", r);
     return PFNL_ERR_CUDA;
   }
-  dim3 grid(Lp / kQT, N);
+  const int ksplit = part != nullptr ? nl_pick_ksplit(N, L, sms) : 1;
+  float* ypart = part;
+  float* ml = part != nullptr ? part + (size_t)ksplit * N * L * kNL : nullptr;
+  dim3 grid(Lp / kQT, N, ksplit);
   if (nsplit == 2)
-    nl_tc_kernel<2><<<grid, kNlThreads, NlCfg<2>::SMEM, s>>>(tmx, tmxl, tmg, tmgl, L, Lp, Y);
+    nl_tc_kernel<2><<<grid, kNlThreads, NlCfg<2>::SMEM, s>>>(tmx, tmxl, tmg, tmgl, L, Lp, Y, ksplit, ypart, ml);
   else
-    nl_tc_kernel<1><<<grid, kNlThreads, NlCfg<1>::SMEM, s>>>(tmx, tmxl, tmg, tmgl, L, Lp, Y);
+    nl_tc_kernel<1><<<grid, kNlThreads, NlCfg<1>::SMEM, s>>>(tmx, tmxl, tmg, tmgl, L, Lp, Y, ksplit, ypart, ml);
   PFNL_LAUNCH_CHECK();
+  *launches_out = 2;
+  if (ksplit > 1) {
+    const long long rows = (long long)N * L;
+    nl_merge_kernel<<<(unsigned)ceil_div(rows * (kNL / 4), 256), 256, 0, s>>>(ypart, ml, ksplit, rows, Y);
+    PFNL_LAUNCH_CHECK();
+    *launches_out = 3;
+  }
   return PFNL_OK;
+}
+
+// floats of key-split scratch for (N, L): partial O [k][N,L,84] + (max, sum) [k][N,L,2]
+static size_t nl_part_floats(int N, int L, int sms) {
+  const int k = nl_pick_ksplit(N, L, sms);
+  return k > 1 ? (size_t)k * N * L * (kNL + 2) : 0;
 }
 
 size_t tc_nl_workspace_bytes(int N, int L) {
   const size_t Lp = (size_t)ceil_div(L, kKT) * kKT;
-  return nl_x_bytes(N, Lp) + nl_g_bytes(N, Lp) + 1024;
+  // the split is chosen for the device's SM count at run time; size the scratch for the largest choice
+  size_t part = 0;
+  for (int sms = 64; sms <= 256; sms += 4) part = std::max(part, nl_part_floats(N, L, sms));
+  return nl_x_bytes(N, Lp) + nl_g_bytes(N, Lp) + (part * 4 + 1023) / 1024 * 1024 + 1024;
 }
 
 int tc_nonlocal(const TcWeights& tw, TcWorkspace& w, const float* tokens, const float* lr, int N, int H, int W,
@@ -516,12 +592,14 @@ int tc_nonlocal(const TcWeights& tw, TcWorkspace& w, const float* tokens, const 
   __half* x16 = (__half*)w.nl_x16;
   __half* gt16 = (__half*)((uint8_t*)w.nl_x16 + nl_x_bytes(N, Lp));
   float* y = (float*)w.nl_priv;
+  float* part = (float*)((uint8_t*)w.nl_x16 + nl_x_bytes(N, Lp) + nl_g_bytes(N, Lp));
+  int nl = 0;
   if (prof) prof->begin(kProfNonlocal, s);
-  int rc = run_nl_tc(nullptr, lr, H, W, N, L, tc_nl_nsplit(tw.precision), x16, gt16, y, s);
+  int rc = run_nl_tc(nullptr, lr, H, W, N, L, tc_nl_nsplit(tw.precision), x16, gt16, y, part, tw.num_sms, s, &nl);
   if (rc == PFNL_OK) rc = launch_nl_linear_scatter(y, lr, N, H, W, tw.raw.nl_gw_w, tw.raw.nl_gw_b, inp21, s);
   if (prof) prof->end(s);
   if (rc) return rc;
-  *launches += 3;
+  *launches += nl + 1;
   return PFNL_OK;
 }
 
@@ -534,23 +612,26 @@ int tc_nonlocal_tokens(const TcWeights& tw, const float* tokens, int N, int L, f
   const size_t b_x = nl_x_bytes(N, Lp);
   const size_t b_g = nl_g_bytes(N, Lp);
   const size_t b_y = ((size_t)N * L * kNL * 4 + 1023) / 1024 * 1024;
-  if (b_x + b_g + b_y > cap) {
+  const size_t b_p = (nl_part_floats(N, L, tw.num_sms) * 4 + 1023) / 1024 * 1024;
+  if (b_x + b_g + b_y + b_p > cap) {
     if (scratch) {
       PFNL_CUDA(cudaDeviceSynchronize());
       PFNL_CUDA(cudaFree(scratch));
       scratch = nullptr;
       cap = 0;
     }
-    PFNL_CUDA(cudaMalloc((void**)&scratch, b_x + b_g + b_y));
-    cap = b_x + b_g + b_y;
+    PFNL_CUDA(cudaMalloc((void**)&scratch, b_x + b_g + b_y + b_p));
+    cap = b_x + b_g + b_y + b_p;
   }
   __half* x16 = (__half*)scratch;
   __half* gt16 = (__half*)(scratch + b_x);
   float* y = (float*)(scratch + b_x + b_g);
-  int rc = run_nl_tc(tokens, nullptr, 0, 0, N, L, tc_nl_nsplit(tw.precision), x16, gt16, y, s);
+  float* part = b_p ? (float*)(scratch + b_x + b_g + b_y) : nullptr;
+  int nl = 0;
+  int rc = run_nl_tc(tokens, nullptr, 0, 0, N, L, tc_nl_nsplit(tw.precision), x16, gt16, y, part, tw.num_sms, s, &nl);
   if (rc == PFNL_OK) rc = launch_nl_linear(y, N * L, tw.raw.nl_gw_w, tw.raw.nl_gw_b, out, s);
   if (rc) return rc;
-  *launches += 3;
+  *launches += nl + 1;
   return PFNL_OK;
 }
 

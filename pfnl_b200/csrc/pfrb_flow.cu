@@ -1,0 +1,660 @@
+// The PFRB stack (model/pfnl.py:65-71, 20 blocks) as ONE persistent dataflow kernel for sm_100a.
+//
+// Why: the MMA rate of a Cout = 64 conv is fixed by the part (profiles/r2a_mma_rate_probe.txt: 147-152 cycles per
+// fp16x3 k-step whether one CTA or a CTA pair issues it), so what the two-launches-per-block kernels of conv_tc.cu
+// lose is everything around the MMAs: 128 of 148 SMs busy (the work unit was "spatial tile x 7 frames" and
+// 16 clips x 32x32 give exactly 128 units), a weight-image swap in the middle of every launch, the fill-bound
+// conv10 phase, and a prologue + tail per launch.  Here every SM runs ONE persistent CTA with ONE role for the
+// whole stack and the four convolutions of a block run concurrently on different SMs, ordered by per-tile
+// arrival counters in global memory instead of kernel boundaries:
+//
+//   role      CTAs/148  work item                 waits for (counter >= target)                 publishes
+//   conv1        64     tile (u,t)  3x3 64->64    block b>0: conv2f(b-1) of the 3x3 neighbour   c1[u]   += 16
+//                                                 tiles of frame t  (halo of its input)
+//   conv10       10     unit u      1x1 448->64   c1[u] = 7 tiles of block b                    c10[u]  += 16
+//   conv2b       10     unit u      3x3 base half c10 of the 3x3 neighbour units (halo of base) c2b[u]  += 16
+//   conv2f       64     tile (u,t)  3x3 frame     c2b[u] (partial sums; transitively the halo   c2f[u,t]+= 16
+//                       half + residual           of inp1)
+//
+// (u = clip x spatial 16x8 tile, t = frame; 16 = one arrival per epilogue warp after its stores are fenced.)
+// Items are striped over the CTAs of a role (item = rank, rank + n_role, ...), every role advances through the
+// units in the same order at the same rate (~9 units per tile time at 16 clips), so the roles run a few tiles
+// apart and the next block starts while the previous one drains: no per-block fill/drain, 148 SMs busy
+// (64 x 14 tiles = 896 exactly for conv1/conv2f; 13 items for conv10/conv2b), one weight image per CTA and
+// block (reloaded between blocks behind the first tile's patch loads), one launch instead of 40.
+//
+// Buffers: inp0 is ping-pong (block b reads A[b&1], writes A[(b+1)&1]) because conv2f(b) of a tile may run
+// before a neighbour's conv1(b) has read its halo; every other write-after-read hazard is ordered by the
+// dependency chain itself (conv1(b+1,u) waits for conv2f(b) of all neighbours of u, which have read inp1(b,u);
+// conv10(b+1,u) follows from conv2b(b, nbr(u)); conv2b(b+1,u) from conv2f(b,u,*)).
+// Cross-CTA visibility: writer = stores, __threadfence, fence.proxy.async, red.release.gpu; reader = ld.acquire.gpu
+// by the producer warp (lane-parallel over the <= 9 counters), fence.proxy.async, then TMA; the one generic-proxy
+// read of another CTA's data (the fp32 partial sums in the conv2f epilogue) is acquired by the reading warp and
+// goes past the L1.  Deadlock freedom: the grid is at most one CTA per SM (all resident), every CTA walks its
+// items in increasing (block, item) order and waits only on items that are earlier in that order for their own
+// role; programmatic launch of the next kernel is triggered only at the end (a dependent grid must never take an
+// SM a CTA of this grid still needs).  All waits are bounded (tc_ptx.cuh).
+//
+// The per-tile arithmetic is the one of conv_tc.cu (conv_tc_dev.cuh): results are bit-identical to the phase
+// kernels (tests/test_gpu_tensorcore.py::test_flow_matches_phase_kernels).
+#include <string.h>
+
+#include "conv_tc_dev.cuh"
+
+namespace pfnl {
+
+namespace {
+
+enum FlowRole { kRoleConv1 = 0, kRoleConv10 = 1, kRoleConv2b = 2, kRoleConv2f = 3 };
+constexpr int kFlowArrivals = kTcEpiWarps;  // a finished tile adds this much to its counter
+constexpr int kFlowThreads = kTcThreads + 64;  // + dependency warp (18) + publisher warp (19)
+
+struct alignas(64) FlowParams {
+  CUtensorMap tmA[2][2];    // inp0 ping-pong buffers [buffer][plane], 3x3 halo box
+  CUtensorMap tmB3[2];      // inp1 [plane], 3x3 halo box  (conv2 frame half)
+  CUtensorMap tmB1[2];      // inp1 [plane], 1x1 box       (conv10)
+  CUtensorMap tmBase[2];    // base [plane], 3x3 halo box  (conv2 base half)
+  const __half* wimg[4][PFNL_NUM_BLOCK];  // [role][block]
+  const float* bias[4][PFNL_NUM_BLOCK];   // [role][block] (conv2b: NULL)
+  __half* actA[2][2];
+  __half* actB[2];
+  __half* base[2];
+  float* pbase;
+  int* flags;        // c1[U] | c10[U] | c2b[U] | c2f[7U] | exit counter
+  int* fault;        // host-mapped, see wait_timeout_trap
+  int* progress;     // host-mapped progress marks, 8 ints per CTA (PFNL_FLOW_DEBUG=1), else NULL
+  long long* trace;  // PFNL_TC_TRACE: per CTA {start ns, end ns, cycles, cycles spent waiting for dependencies}
+  int H, W, tiles_x, tiles_y, n_units;
+  int blk0, nblk, buf0;
+  int n_role[4];
+};
+
+template <int NSPLIT>
+struct FlowCfg {
+  using C3 = PhaseCfg<3, 1, 64, NSPLIT == 2 ? 2 : 1>;
+  using C10 = PhaseCfg<1, 7, 64, 1>;
+  static constexpr int CTRL_BYTES = 8192;
+  static constexpr int W3 = C3::NTAPS * NSPLIT * C3::WT_BYTES;     // 147456 (split) / 73728
+  static constexpr int W10 = C10::NTAPS * NSPLIT * C10::WT_BYTES;  // 114688 (split) / 57344
+  static constexpr int SLOT3 = (C3::PATCH_BYTES + 1023) / 1024 * 1024;
+  static constexpr int SLOT10 = C10::PATCH_BYTES;
+  static constexpr int SMEM_MAX = 227 * 1024;
+  static constexpr int AVAIL = SMEM_MAX - 1024 - CTRL_BYTES;
+  static constexpr int NS3 = (AVAIL - W3) / SLOT3 > 6 ? 6 : (AVAIL - W3) / SLOT3;
+  static constexpr int NS10 = (AVAIL - W10) / SLOT10 > 8 ? 8 : (AVAIL - W10) / SLOT10;
+  static constexpr int SMEM_BYTES = 1024 + CTRL_BYTES + cmax(W3 + NS3 * SLOT3, W10 + NS10 * SLOT10);
+  static constexpr int CH_STRIDE = NSPLIT == 2 ? 128 : 64;
+  static constexpr int TMEM_BUF_COLS = C3::NCH * CH_STRIDE;
+  static constexpr int TMEM_NEED = 2 * TMEM_BUF_COLS;
+  static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
+  static_assert(NS3 >= 3 && NS10 >= 3, "shared memory budget too small");
+  static_assert(SMEM_BYTES <= SMEM_MAX, "shared memory overflow");
+  static_assert(SLOT10 % 1024 == 0 && W3 % 1024 == 0 && W10 % 1024 == 0, "ring slots must stay 1 KB aligned");
+};
+
+struct FlowCtrl {
+  TcBars bars;
+  uint64_t wfull;  // weight image of the current block has landed
+  uint64_t wfree;  // all MMAs of the finished block are complete (the image may be overwritten)
+  uint64_t stored[2];   // the 16 epilogue warps have issued the stores of tile it (slot it & 1)
+  uint64_t pubfree[2];  // the publisher warp has consumed that slot
+  uint32_t tmem_base;
+  int last_cta;
+  int deps_seen;  // items whose inputs the producer warp has acquired (gpu scope); read by the epilogue warps
+  float bias[PFNL_NUM_BLOCK][64];
+};
+static_assert(sizeof(FlowCtrl) <= 8192, "FlowCtrl does not fit its slot");
+
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {  // strong load (L2), no fence: poll with this
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct FlowItem {
+  int u, t, tx, ty, nimg;
+};
+__device__ __forceinline__ FlowItem flow_item(const FlowParams& p, int role, int item) {
+  FlowItem f;
+  const bool per_frame = role == kRoleConv1 || role == kRoleConv2f;
+  f.u = per_frame ? item / kFrames : item;
+  f.t = per_frame ? item - f.u * kFrames : 0;
+  f.tx = f.u % p.tiles_x;
+  const int r = f.u / p.tiles_x;
+  f.ty = r % p.tiles_y;
+  f.nimg = r / p.tiles_y;
+  return f;
+}
+
+// Whole producer warp: have the inputs of item f of (launch-relative) block b been published?  Lane-parallel
+// acquire loads of the <= 9 counters; on success the warp may issue the item's TMA loads.
+__device__ __forceinline__ bool flow_deps_ready(const FlowParams& p, int role, int b, const FlowItem& f, int lane,
+                                                bool blocking, long long& wait_cycles) {
+  const int U = p.n_units;
+  const int* ptr = nullptr;
+  int target = 0;
+  if (role == kRoleConv10) {
+    if (lane == 0) {
+      ptr = p.flags + f.u;
+      target = kFlowArrivals * kFrames * (b + 1);
+    }
+  } else if (role == kRoleConv2f) {
+    if (lane == 0) {
+      ptr = p.flags + 2 * U + f.u;
+      target = kFlowArrivals * (b + 1);
+    }
+  } else if (lane < 9 && (role == kRoleConv2b || b > 0)) {
+    const int ty = f.ty + lane / 3 - 1, tx = f.tx + lane % 3 - 1;
+    if (ty >= 0 && ty < p.tiles_y && tx >= 0 && tx < p.tiles_x) {
+      const int v = (f.nimg * p.tiles_y + ty) * p.tiles_x + tx;
+      if (role == kRoleConv2b) {
+        ptr = p.flags + U + v;
+        target = kFlowArrivals * (b + 1);
+      } else {
+        ptr = p.flags + 3 * U + v * kFrames + f.t;
+        target = kFlowArrivals * b;
+      }
+    }
+  }
+  bool ok = ptr == nullptr || ld_relaxed_gpu(ptr) >= target;
+  bool all = __all_sync(0xffffffffu, ok);
+  if (!all && blocking) {
+    const long long t0 = clock64();
+    do {
+      __nanosleep(40);
+      if (!ok) ok = ld_relaxed_gpu(ptr) >= target;
+      all = __all_sync(0xffffffffu, ok);
+      if (!all && clock64() - t0 > kTcWaitLimitCycles) wait_timeout_trap(p.fault, 1 + role, b, f.u * kFrames + f.t);
+    } while (!all);
+    wait_cycles += clock64() - t0;
+  }
+  if (all) {
+    // acquire: the polls were relaxed; one gpu-scope fence orders everything the publishers released before this
+    // warp's subsequent accesses (the __all_sync above carries the other lanes' observations to every lane), the
+    // proxy fence orders other CTAs' generic-proxy stores before this CTA's TMA (async proxy) reads
+    __threadfence();
+    fence_proxy_async_all();
+  }
+  return all;
+}
+
+// One CTA of role `role` (rank `rank` of p.n_role[role]); PC/NS/SLOT/WB describe the role's conv shape, patch ring
+// and weight-image size.
+template <int NSPLIT, class PC, int NS, int SLOT, int WB>
+__device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int role, int rank) {
+  using FC = FlowCfg<NSPLIT>;
+  FlowCtrl* ctl = reinterpret_cast<FlowCtrl*>(smem);
+  uint8_t* wsm = smem + FC::CTRL_BYTES;  // weight image of the running block
+  uint8_t* ring = wsm + WB;              // [NS][SLOT]
+  TcBars* bars = &ctl->bars;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nr = p.n_role[role];
+  const bool per_frame = role == kRoleConv1 || role == kRoleConv2f;
+  const int n_items = per_frame ? p.n_units * kFrames : p.n_units;
+  const bool has_work = rank < n_items;
+  constexpr int PAD = (PC::KS - 1) / 2;
+
+  // ---- prologue: touches only weights / biases (never written by any kernel); overlaps the previous
+  //      kernel's tail under programmatic dependent launch
+  if (tid == 0) {
+    mbar_init(&ctl->wfull, 1);
+    mbar_init(&ctl->wfree, 1);
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&bars->full[i], 1);
+      mbar_init(&bars->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->tmem_full[i], 1);
+      mbar_init(&bars->tmem_empty[i], kTcEpiWarps);
+      mbar_init(&ctl->stored[i], kTcEpiWarps);
+      mbar_init(&ctl->pubfree[i], 1);
+    }
+    fence_mbar_init();
+    fence_proxy_async();
+    ctl->last_cta = 0;
+    ctl->deps_seen = 0;
+    if (has_work) {
+      mbar_arrive_expect_tx(&ctl->wfull, WB);
+      load_weights<WB>(wsm, p.wimg[role][p.blk0], &ctl->wfull);
+    }
+  }
+  for (int i = tid; i < p.nblk * 64; i += kFlowThreads) {
+    const float* bp = p.bias[role][p.blk0 + (i >> 6)];
+    ctl->bias[i >> 6][i & 63] = bp != nullptr ? bp[i & 63] : 0.f;
+  }
+  if (warp == 1) {
+    tmem_alloc(&ctl->tmem_base, FC::TMEM_COLS);
+    tmem_relinquish();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = ctl->tmem_base;
+  pdl_wait();  // the previous kernel's activations are visible after this
+  long long t_start = 0, c_start = 0, wait_cycles = 0;
+  int* prog = p.progress != nullptr ? p.progress + 8 * blockIdx.x : nullptr;
+  auto mark = [&](int slot, int state, int b, int item) {  // slot 0: producer, 4: epilogue
+    if (prog != nullptr && lane == 0) {
+      volatile int* q = prog;
+      q[slot + 0] = state;
+      q[slot + 1] = b;
+      q[slot + 2] = item;
+    }
+  };
+  if (prog != nullptr && tid == 0) prog[7] = role + 1;
+  // PFNL_TC_TRACE: rank 0 of every role stamps its first 31 tiles (clock64): [0,64) producer (inputs published,
+  // loads issued), [64,128) MMA warp (data ready, issue done), [128,192) epilogue (accumulator ready, stores
+  // issued), [192,256) epilogue (counter published)
+  long long* tr = (p.trace != nullptr && rank == 0) ? p.trace + 4 * 256 + role * 256 : nullptr;
+  if (tr != nullptr && tid == 0) tr[63] = clock64();
+  int ptile = 0;
+  if (p.trace != nullptr && tid == 0) {
+    t_start = globaltimer_ns();
+    c_start = clock64();
+  }
+
+  if (has_work) {
+    if (warp == 0) {
+      // ===================== TMA producer (one thread) =====================
+      // Issues an item's patch loads once the dependency warp has acquired its inputs (ctl->deps_seen, shared
+      // memory: the gpu-scope polls and fences cost 2-3 K cycles per item and run ahead on their own warp).
+      if (lane == 0) {
+        TcRing rg{0, 0};
+        int nissued = 0;
+        auto seen = [&]() {
+          int v;
+          asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&ctl->deps_seen)) : "memory");
+          return v;
+        };
+        for (int b = 0; b < p.nblk; ++b) {
+          const int pp = (p.buf0 + b) & 1;  // inp0 buffer this block reads
+          const CUtensorMap* tm_hi = role == kRoleConv1    ? &p.tmA[pp][0]
+                                     : role == kRoleConv10 ? &p.tmB1[0]
+                                     : role == kRoleConv2b ? &p.tmBase[0]
+                                                           : &p.tmB3[0];
+          const CUtensorMap* tm_lo = role == kRoleConv1    ? &p.tmA[pp][1]
+                                     : role == kRoleConv10 ? &p.tmB1[1]
+                                     : role == kRoleConv2b ? &p.tmBase[1]
+                                                           : &p.tmB3[1];
+          auto issue = [&](const FlowItem& f) {
+            if (tr != nullptr && ptile < 31) tr[2 * ptile] = clock64();
+            load_tile<PC, NSPLIT, NS, SLOT>(tm_hi, tm_lo, ring, bars, rg, f.tx * 8 - PAD, f.ty * 16 - PAD,
+                                            per_frame ? f.nimg * kFrames + f.t
+                                                      : f.nimg * (role == kRoleConv10 ? kFrames : 1));
+            if (tr != nullptr && ptile < 31) tr[2 * ptile + 1] = clock64();
+            ++ptile;
+            ++nissued;
+          };
+          int item = rank;
+          if (b > 0) {
+            // everything that enters shared memory shares one queue: the first tile's patches go in front of the
+            // weight image when its inputs are already there
+            // (only when the whole tile fits the ring: the MMA warp frees no slot before the image has landed -
+            //  the 14 loads of a conv10 tile would wait for each other)
+            if (PC::NSRC * NSPLIT <= NS && seen() > nissued) {
+              issue(flow_item(p, role, item));
+              item += nr;
+            }
+            mark(0, 3, b, item);
+            mbar_wait(&ctl->wfree, (b - 1) & 1, p.fault);
+            mbar_arrive_expect_tx(&ctl->wfull, WB);
+            load_weights<WB>(wsm, p.wimg[role][p.blk0 + b], &ctl->wfull);
+          }
+          if (b + 1 < p.nblk && rank * 16384 < WB) {  // warm the L2 with the next block's image
+            const int off = rank * 16384;
+            l2_prefetch_bulk(reinterpret_cast<const uint8_t*>(p.wimg[role][p.blk0 + b + 1]) + off,
+                             (WB - off) < 16384 ? (WB - off) : 16384);
+          }
+          for (; item < n_items; item += nr) {
+            mark(0, 1, b, item);
+            if (seen() <= nissued) {
+              const long long t0 = clock64();
+              while (seen() <= nissued) {
+                __nanosleep(32);
+                if (clock64() - t0 > kTcWaitLimitCycles) wait_timeout_trap(p.fault, 6, b, item);
+              }
+              wait_cycles += clock64() - t0;
+            }
+            mark(0, 2, b, item);
+            issue(flow_item(p, role, item));
+          }
+          mark(0, 4, b, item);
+        }
+        if (p.trace != nullptr) p.trace[4 * blockIdx.x + 3] = wait_cycles;
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer (converged warp) =====================
+      TcRing rg{0, 0};
+      int it = 0;
+      for (int b = 0; b < p.nblk; ++b) {
+        mbar_wait(&ctl->wfull, b & 1, p.fault);
+        fence_after_sync();
+        for (int item = rank; item < n_items; item += nr, ++it) {
+          if (prog != nullptr && lane == 0) *(volatile int*)(prog + 3) = it + 1;
+          mma_tile<PC, NSPLIT, NS, SLOT, FC::TMEM_BUF_COLS, FC::CH_STRIDE>(wsm, ring, bars, tmem, rg, it, lane, tr);
+        }
+        if (b + 1 < p.nblk) {
+          if (elect_one()) mma_commit(&ctl->wfree);  // arrives when every MMA issued so far has completed
+          __syncwarp();
+        }
+      }
+    } else if (warp < 2 + kTcEpiWarps) {
+      // ===================== epilogue (warps 2..17) =====================
+      int it = 0;
+      U256 pre[2];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pre[0].w[j] = pre[1].w[j] = 0u;
+      // Publishing a tile (stores visible device-wide and to the TMA engines of other SMs, then the arrival on
+      // its counter) is NOT done here: 512 threads fencing after every tile cost 3-6 K cycles per tile (measured,
+      // profiles/r2b_flow_trace_first.txt) and made the epilogue, not the MMAs, set the tile period.  The epilogue
+      // warps only hand the tile to the publisher warp through an mbarrier (release at CTA scope).
+      TcNoHook nohook;
+      for (int b = 0; b < p.nblk; ++b) {
+        const int pp = (p.buf0 + b) & 1;
+        TcEpiArgs E;
+        E.epi = role == kRoleConv2b ? kEpiPartialF32 : (role == kRoleConv2f ? kEpiResPlanes : kEpiActPlanes);
+        E.accumulate = 0;
+        E.f32_chunked = 1;
+        E.coherent_pbase = 1;
+        E.pbase = p.pbase;
+        E.out_hi = role == kRoleConv1 ? p.actB[0] : (role == kRoleConv10 ? p.base[0] : p.actA[pp ^ 1][0]);
+        E.out_lo = role == kRoleConv1 ? p.actB[1] : (role == kRoleConv10 ? p.base[1] : p.actA[pp ^ 1][1]);
+        E.res_hi = p.actA[pp][0];
+        E.res_lo = p.actA[pp][1];
+        E.out_f32 = p.pbase;
+        E.H = p.H;
+        E.W = p.W;
+        for (int item = rank; item < n_items; item += nr, ++it) {
+          const FlowItem f = flow_item(p, role, item);
+          if (warp == 2) mark(4, 1, b, item);
+          if (role == kRoleConv2f) {
+            // the partial sums of this unit come from a conv2b CTA and are read with generic loads: wait until the
+            // producer warp has acquired this item's counters (CTA-scope acquire of its count; the loads
+            // themselves go past the L1, conv_tc_dev.cuh)
+            auto seen = [&]() {
+              int v;
+              asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&ctl->deps_seen)) : "memory");
+              return v;
+            };
+            if (__any_sync(0xffffffffu, seen() <= it)) {
+              const long long t0 = clock64();
+              while (seen() <= it) {
+                __nanosleep(64);
+                if (clock64() - t0 > kTcWaitLimitCycles) wait_timeout_trap(p.fault, 5, b, item);
+              }
+            }
+            __syncwarp();
+          }
+          epi_tile<PC, NSPLIT, FC::TMEM_BUF_COLS, FC::CH_STRIDE>(E, bars, ctl->bias[b], tmem, it, warp, lane,
+                                                                 per_frame ? f.nimg * kFrames + f.t : f.nimg, f.nimg,
+                                                                 f.tx, f.ty, true, pre, tr, nohook);
+          // hand the tile to the publisher warp (slot it & 1; wait until it has consumed the slot's previous tile)
+          __syncwarp();
+          if (lane == 0) {
+            mbar_wait(&ctl->pubfree[it & 1], ((it >> 1) & 1) ^ 1, p.fault);
+            mbar_arrive(&ctl->stored[it & 1]);
+          }
+          if (warp == 2) mark(4, 3, b, item);
+        }
+      }
+    } else if (warp == 2 + kTcEpiWarps) {
+      // ===================== dependency warp (warp 18) =====================
+      // Walks the CTA's item sequence ahead of everybody else: lane-parallel relaxed polls of the <= 9 counters an
+      // item waits for, one gpu-scope acquire fence + proxy fence per item, then the count of acquired items goes
+      // to shared memory (release at CTA scope) for the TMA thread and the conv2 epilogue warps.
+      int nseen = 0;
+      long long dummy = 0;
+      for (int b = 0; b < p.nblk; ++b)
+        for (int item = rank; item < n_items; item += nr) {
+          const FlowItem f = flow_item(p, role, item);
+          flow_deps_ready(p, role, b, f, lane, true, dummy);
+          ++nseen;
+          if (lane == 0)
+            asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(&ctl->deps_seen)), "r"(nseen)
+                         : "memory");
+          __syncwarp();
+        }
+    } else if (lane == 0) {
+      // ===================== publisher (warp 19, one thread) =====================
+      // waits until the 16 epilogue warps have issued a tile's stores (acquire at CTA scope of their release),
+      // makes them visible at gpu scope and to the async proxy, then adds the tile's arrivals to its counter.
+      // One thread fences for the CTA (the cooperative-groups grid-barrier pattern); its latency stalls nobody.
+      const int U = p.n_units;
+      int it = 0;
+      for (int b = 0; b < p.nblk; ++b)
+        for (int item = rank; item < n_items; item += nr, ++it) {
+          const FlowItem f = flow_item(p, role, item);
+          int* done = p.flags + (role == kRoleConv1    ? f.u
+                                 : role == kRoleConv10 ? U + f.u
+                                 : role == kRoleConv2b ? 2 * U + f.u
+                                                       : 3 * U + f.u * kFrames + f.t);
+          mbar_wait(&ctl->stored[it & 1], (it >> 1) & 1, p.fault);
+          fence_proxy_async_all();
+          red_release_gpu_add(done, kFlowArrivals);  // release at gpu scope: cumulative over the epilogue warps' stores
+          mbar_arrive(&ctl->pubfree[it & 1]);
+          if (tr != nullptr && it < 64) tr[192 + it] = clock64();
+        }
+    }
+  }
+  pdl_launch_dependents();  // only now: a dependent grid must not occupy an SM this grid still needs
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, FC::TMEM_COLS);
+  // ---- the last CTA to finish clears the counters for the next launch
+  const int n_flags = 10 * p.n_units;
+  if (tid == 0) {
+    if (p.trace != nullptr) {
+      p.trace[4 * blockIdx.x + 0] = t_start;
+      p.trace[4 * blockIdx.x + 1] = globaltimer_ns();
+      p.trace[4 * blockIdx.x + 2] = clock64() - c_start;
+    }
+    __threadfence();
+    ctl->last_cta = atomicAdd(p.flags + n_flags, 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (ctl->last_cta) {
+    __threadfence();
+    for (int i = tid; i <= n_flags; i += kFlowThreads) p.flags[i] = 0;
+  }
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kFlowThreads, 1) pfrb_flow_kernel(const __grid_constant__ FlowParams p) {
+  using FC = FlowCfg<NSPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  int role = 0, rank = blockIdx.x;
+  while (role < 3 && rank >= p.n_role[role]) {
+    rank -= p.n_role[role];
+    ++role;
+  }
+  if (role == kRoleConv10)
+    flow_cta<NSPLIT, typename FC::C10, FC::NS10, FC::SLOT10, FC::W10>(p, smem, role, rank);
+  else
+    flow_cta<NSPLIT, typename FC::C3, FC::NS3, FC::SLOT3, FC::W3>(p, smem, role, rank);
+}
+
+bool flow_tracing() {
+  static const bool on = getenv("PFNL_TC_TRACE") != nullptr;
+  return on;
+}
+
+template <int NSPLIT>
+int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int buf0, int N, int H, int W, bool pdl,
+                cudaStream_t s) {
+  using FC = FlowCfg<NSPLIT>;
+  FlowParams p;
+  memset(&p, 0, sizeof(p));
+  const int images = N * kFrames;
+  int r = 0;
+  for (int pl = 0; pl < 2 && r == 0; ++pl) {
+    const int sp = pl < NSPLIT ? pl : 0;  // fp16 mode: the lo maps alias the hi plane (never used)
+    r = make_act_tmap(&p.tmA[0][pl], w.actA[sp], images, H, W, FC::C3::BOX_W, FC::C3::BOX_H);
+    if (r == 0) r = make_act_tmap(&p.tmA[1][pl], w.actA2[sp], images, H, W, FC::C3::BOX_W, FC::C3::BOX_H);
+    if (r == 0) r = make_act_tmap(&p.tmB3[pl], w.actB[sp], images, H, W, FC::C3::BOX_W, FC::C3::BOX_H);
+    if (r == 0) r = make_act_tmap(&p.tmB1[pl], w.actB[sp], images, H, W, FC::C10::BOX_W, FC::C10::BOX_H);
+    if (r == 0) r = make_act_tmap(&p.tmBase[pl], w.base[sp], N, H, W, FC::C3::BOX_W, FC::C3::BOX_H);
+  }
+  if (r != 0) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for N=%d H=%d W=%d", r, N, H, W);
+    return PFNL_ERR_CUDA;
+  }
+  for (int i = 0; i < PFNL_NUM_BLOCK; ++i) {
+    p.wimg[kRoleConv1][i] = (const __half*)tw.conv1[i];
+    p.wimg[kRoleConv10][i] = (const __half*)tw.conv10[i];
+    p.wimg[kRoleConv2b][i] = (const __half*)tw.conv2b[i];
+    p.wimg[kRoleConv2f][i] = (const __half*)tw.conv2f[i];
+    p.bias[kRoleConv1][i] = tw.raw.conv1_b[i];
+    p.bias[kRoleConv10][i] = tw.raw.conv10_b[i];
+    p.bias[kRoleConv2b][i] = nullptr;
+    p.bias[kRoleConv2f][i] = tw.raw.conv2_b[i];
+  }
+  for (int pl = 0; pl < 2; ++pl) {
+    p.actA[0][pl] = (__half*)w.actA[pl];
+    p.actA[1][pl] = (__half*)w.actA2[pl];
+    p.actB[pl] = (__half*)w.actB[pl];
+    p.base[pl] = (__half*)w.base[pl];
+  }
+  p.pbase = w.pbase;
+  p.flags = w.flow_flags;
+  p.fault = w.flow_fault;
+  static const bool dbg = getenv("PFNL_FLOW_DEBUG") != nullptr;
+  p.progress = (dbg && w.flow_fault != nullptr) ? w.flow_fault + 8 : nullptr;
+  p.H = H;
+  p.W = W;
+  p.tiles_x = ceil_div(W, 8);
+  p.tiles_y = ceil_div(H, 16);
+  p.n_units = N * p.tiles_x * p.tiles_y;
+  p.blk0 = blk0;
+  p.nblk = nblk;
+  p.buf0 = buf0;
+  // role split of the grid ~ MMA work per block (conv1 252 : conv10 28 : conv2b 36 : conv2f 252 k-steps per
+  // unit), conv10 rounded up because its tiles are fill-bound: 64 / 10 / 10 / 64 of 148
+  const int G = tw.num_sms;
+  const int n1 = G * 64 / 148;
+  const int rem = G - 2 * n1;
+  p.n_role[kRoleConv1] = n1;
+  p.n_role[kRoleConv2f] = n1;
+  p.n_role[kRoleConv2b] = (rem + 1) / 2;
+  p.n_role[kRoleConv10] = rem - (rem + 1) / 2;
+  {  // PFNL_FLOW_SPLIT="conv1,conv10,conv2b,conv2f" (CTAs per role, sum <= SM count): experiments only
+    static const char* env = getenv("PFNL_FLOW_SPLIT");
+    int a = 0, b = 0, c = 0, d = 0;
+    if (env != nullptr && sscanf(env, "%d,%d,%d,%d", &a, &b, &c, &d) == 4 && a > 0 && b > 0 && c > 0 && d > 0 &&
+        a + b + c + d <= G) {
+      p.n_role[kRoleConv1] = a;
+      p.n_role[kRoleConv10] = b;
+      p.n_role[kRoleConv2b] = c;
+      p.n_role[kRoleConv2f] = d;
+    }
+  }
+  const int grid = p.n_role[0] + p.n_role[1] + p.n_role[2] + p.n_role[3];
+  if (n1 < 1 || p.n_role[kRoleConv10] < 1) {
+    set_error("pfrb flow kernel needs at least 8 SMs (device has %d)", G);
+    return PFNL_ERR_UNSUPPORTED_ARCH;
+  }
+  static long long* trace_dev = nullptr;
+  if (flow_tracing()) {
+    if (!trace_dev) PFNL_CUDA(cudaMalloc((void**)&trace_dev, (4 * 256 + 4 * 256) * sizeof(long long)));
+    PFNL_CUDA(cudaMemsetAsync(trace_dev, 0, (4 * 256 + 4 * 256) * sizeof(long long), s));
+    p.trace = trace_dev;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kFlowThreads);
+  cfg.dynamicSmemBytes = FC::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl && !flow_tracing()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  PFNL_CUDA(cudaLaunchKernelEx(&cfg, pfrb_flow_kernel<NSPLIT>, p));
+  if (flow_tracing()) {
+    static long long t[4 * 256 + 4 * 256];
+    PFNL_CUDA(cudaStreamSynchronize(s));
+    PFNL_CUDA(cudaMemcpy(t, trace_dev, sizeof(t), cudaMemcpyDeviceToHost));
+    long long first = 0, last = 0;
+    for (int c = 0; c < grid && c < 256; ++c) {
+      if (t[4 * c] && (first == 0 || t[4 * c] < first)) first = t[4 * c];
+      if (t[4 * c + 1] > last) last = t[4 * c + 1];
+    }
+    fprintf(stderr, "[flow-trace] NSPLIT=%d blocks=%d units=%d grid=%d span %.2f us\n", NSPLIT, nblk, p.n_units, grid,
+            (last - first) / 1e3);
+    const char* names[4] = {"conv1", "conv10", "conv2b", "conv2f"};
+    int c = 0;
+    for (int role = 0; role < 4; ++role) {
+      double dsum = 0, dmax = 0, csum = 0, wsum = 0, wmax = 0, smax = 0, emin = 1e30;
+      const int n = p.n_role[role];
+      for (int k = 0; k < n && c < 256; ++k, ++c) {
+        const double d = (t[4 * c + 1] - t[4 * c]) / 1e3;
+        dsum += d;
+        if (d > dmax) dmax = d;
+        csum += (double)t[4 * c + 2];
+        wsum += (double)t[4 * c + 3];
+        if ((double)t[4 * c + 3] > wmax) wmax = (double)t[4 * c + 3];
+        if ((t[4 * c] - first) / 1e3 > smax) smax = (t[4 * c] - first) / 1e3;
+        if ((t[4 * c + 1] - first) / 1e3 < emin) emin = (t[4 * c + 1] - first) / 1e3;
+      }
+      {
+        const long long* q = t + 4 * 256 + role * 256;
+        const long long z = q[63];
+        fprintf(stderr, "  %-6s rank 0, cycles since its start; producer (inputs published, loads issued):", names[role]);
+        for (int i = 0; i < 16 && q[2 * i + 1]; ++i) fprintf(stderr, " (%lld,%lld)", q[2 * i] - z, q[2 * i + 1] - z);
+        fprintf(stderr, "\n         mma (data ready, issue done):");
+        for (int i = 0; i < 16 && q[64 + 2 + 2 * i]; ++i)
+          fprintf(stderr, " (%lld,%lld)", q[64 + 1 + 2 * i] - z, q[64 + 2 + 2 * i] - z);
+        fprintf(stderr, "\n         epilogue (accumulator ready, stores issued, counter published):");
+        for (int i = 0; i < 16 && q[128 + 2 * i + 1]; ++i)
+          fprintf(stderr, " (%lld,%lld,%lld)", q[128 + 2 * i] - z, q[128 + 2 * i + 1] - z, q[192 + i] - z);
+        fprintf(stderr, "\n");
+      }
+      fprintf(stderr,
+              "  %-6s x%3d: CTA duration avg %.2f max %.2f us (avg %.0f cycles), latest start +%.2f us, earliest end "
+              "+%.2f us, producer waited for dependencies avg %.0f max %.0f cycles\n",
+              names[role], n, dsum / n, dmax, csum / n, smax, emin, wsum / n, wmax);
+    }
+  }
+  return PFNL_OK;
+}
+
+}  // namespace
+
+int tc_flow_init() {
+  PFNL_CUDA(cudaFuncSetAttribute(pfrb_flow_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 FlowCfg<1>::SMEM_BYTES));
+  PFNL_CUDA(cudaFuncSetAttribute(pfrb_flow_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 FlowCfg<2>::SMEM_BYTES));
+  return PFNL_OK;
+}
+
+size_t tc_flow_flag_ints(int N, int H, int W) { return (size_t)10 * N * ceil_div(W, 8) * ceil_div(H, 16) + 1; }
+
+bool tc_flow_default() {
+  static const bool off = getenv("PFNL_TC_FLOW") != nullptr && getenv("PFNL_TC_FLOW")[0] == '0';
+  return !off;
+}
+
+int tc_pfrb_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int buf0, int N, int H, int W, bool pdl,
+                 cudaStream_t s) {
+  if (blk0 < 0 || nblk < 1 || blk0 + nblk > PFNL_NUM_BLOCK) {
+    set_error("tc_pfrb_flow: blocks [%d,%d) out of range", blk0, blk0 + nblk);
+    return PFNL_ERR_BAD_ARG;
+  }
+  if (w.flow_flags == nullptr) {
+    set_error("tc_pfrb_flow: dependency counters are not allocated");
+    return PFNL_ERR_BAD_ARG;
+  }
+  if (tw.nsplit == 2) return launch_flow<2>(tw, w, blk0, nblk, buf0, N, H, W, pdl, s);
+  return launch_flow<1>(tw, w, blk0, nblk, buf0, N, H, W, pdl, s);
+}
+
+}  // namespace pfnl

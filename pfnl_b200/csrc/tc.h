@@ -61,6 +61,8 @@ struct TcWeights {
   void* merge1 = nullptr;
   void* conv0 = nullptr;  // [10 k-chunks][nsplit*64 rows][8 k] fp16, un-swizzled core matrices (conv0_tc_kernel)
   float* zero_bias = nullptr;  // [64] zeros
+  bool flow = true;            // PFRB stack as the persistent dataflow kernel (pfnl_set_flow / PFNL_TC_FLOW=0: phase kernels)
+  int num_sms = 0;             // SM count of the handle's device (grid size of the persistent kernels)
   // non-local (precision 2): fp16 Wg^T image etc.
   void* nl_priv = nullptr;
 };
@@ -68,11 +70,14 @@ struct TcWeights {
 struct TcWorkspace {
   // activations as fp16 NHWC planes [images,H,W,64]; plane 0 = hi, plane 1 = lo (x3 mode)
   void* actA[2];   // inp0 (residual stream)
+  void* actA2[2];  // second inp0 buffer: the dataflow kernel (pfrb_flow.cu) ping-pongs between actA and actA2
   void* actB[2];   // inp1
   void* base[2];   // conv10 output [N,H,W,64]
   float* pbase;    // fp32 partial conv2 over the base half [N,H,W,64]
   void* nl_x16;    // fp16 token matrix [N*L,96]
   void* nl_priv;
+  int* flow_flags;  // dependency counters of pfrb_flow.cu (handle-owned, zero between launches)
+  int* flow_fault;  // host-mapped {1+kind, cta, a, b} of a wait that timed out (survives the trap)
 };
 
 void tc_carve(TcWorkspace& w, int precision, int N, int H, int W, const std::function<char*(size_t)>& take);
@@ -94,8 +99,22 @@ int tc_nonlocal(const TcWeights& tw, TcWorkspace& w, const float* tokens, const 
 // tokens [N,L,84] -> NonLocalBlock output [N,L,84]
 int tc_nonlocal_tokens(const TcWeights& tw, const float* tokens, int N, int L, float* out, cudaStream_t s,
                        long long* launches);
+// The PFRB stack as one persistent dataflow kernel (pfrb_flow.cu): blocks [blk0, blk0+nblk) on the fp16 planes;
+// input in inp0 buffer `buf0` (0 = actA, 1 = actA2), output in buffer (buf0 + nblk) & 1.
+int* tc_fault_buffer();  // api.cu: host-mapped wait-timeout record (device pointer; may be NULL)
+int tc_flow_init();
+bool tc_flow_default();                          // false with PFNL_TC_FLOW=0 in the environment
+size_t tc_flow_flag_ints(int N, int H, int W);   // ints of dependency counters the launch needs (zeroed once)
+int tc_pfrb_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int buf0, int N, int H, int W, bool pdl,
+                 cudaStream_t s);
 // One PFRB with fp32 frames in/out (conversion kernels around the tensor-core block).
 int tc_pfrb_fp32io(const TcWeights& tw, TcWorkspace& w, int precision, int blk, const float* frames, int N, int H,
                    int W, float* frames_out, cudaStream_t s, long long* launches);
+
+// conv0 / convmerge1 alone, fp32 tensors either side (stage-level parity of the tcgen05 kernels)
+int tc_conv0_fp32io(const TcWeights& tw, TcWorkspace& w, int precision, const float* inp21, int N, int H, int W,
+                    float* frames_out, cudaStream_t s, long long* launches);
+int tc_merge1_fp32io(const TcWeights& tw, TcWorkspace& w, int precision, const float* frames, int N, int H, int W,
+                     float* merge, cudaStream_t s, long long* launches);
 
 }  // namespace pfnl

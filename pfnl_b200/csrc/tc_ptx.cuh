@@ -34,8 +34,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Every wait of the tensor-core kernels is bounded: a protocol mistake (or a CTA that never became resident)
+// ends the kernel with a trap - the host sees a launch failure - instead of hanging the device.  The limit is
+// far above anything a correct run reaches (a whole forward is ~2e6 cycles; compute-sanitizer runs are ~100x
+// slower, hence the generous value).  `fault` (optional, host-mapped memory so that it survives the trap)
+// receives {1 + kind, blockIdx.x, a, b} of the first wait that gave up.
+constexpr long long kTcWaitLimitCycles = 6000000000ll;
+static __device__ __noinline__ void wait_timeout_trap(int* fault, int kind, int a, int b) {
+  if (fault != nullptr && atomicCAS(fault, 0, 1 + kind) == 0) {
+    fault[1] = (int)blockIdx.x;
+    fault[2] = a;
+    fault[3] = b;
+    __threadfence_system();
+  }
+  for (int i = 0; i < 64; ++i) __nanosleep(1000000);  // let the record (another lane's, perhaps) reach the host
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* fault = nullptr) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kTcWaitLimitCycles) wait_timeout_trap(fault, 0, (int)smem_u32(bar), (int)parity);
   }
 }
 
@@ -91,44 +110,11 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                : "memory");
 }
 
-// Same, delivered to the same smem offset of every CTA in `cta_mask` of the cluster; each
-// destination CTA's mbarrier (same offset) receives the complete_tx for the bytes it got.
-__device__ __forceinline__ void bulk_load_multicast(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
-                                                    uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-      ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
-      : "memory");
-}
-
-// ---- thread-block clusters ------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_nctarank() {
-  uint32_t v;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(v));
-  return v;
-}
+// ---- thread-block clusters (probes/mma_rate_probe.cu: cta_group::2) ---------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t v;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(v));
   return v;
-}
-// arrive (release at cluster scope) on the mbarrier at the same smem offset in CTA `cta_rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta_rank) {
-  uint32_t raddr;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta_rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {  // acquire at cluster scope
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  }
 }
 __device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA of the cluster
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");

@@ -104,7 +104,11 @@ class Engine:
         return int(lib.pfnl_launch_count(self._h))
 
     PROF_KINDS = ("pack_tokens", "nonlocal", "conv0", "conv1_3x3", "conv10_1x1", "conv2_3x3", "convmerge1",
-                  "tail", "other")
+                  "tail", "other", "pfrb_flow")
+
+    def set_flow(self, enable):
+        """Tensor-core precisions: PFRB stack as one persistent dataflow kernel (default) or two launches per block."""
+        check(lib.pfnl_set_flow(self._h, 1 if enable else 0))
 
     def profile(self, enable):
         """Bracket every launch class with CUDA events (bypasses CUDA graphs while on)."""
@@ -283,8 +287,29 @@ class Engine:
     def pfrb(self, blk, frames, n, h, w):
         """frames [N*7,H,W,64] -> one Progressive Fusion Residual Block (pfnl.py:66-71)."""
         self._chk_in(frames, 4)
+        if tuple(frames.shape) != (n * _lib.NUM_FRAMES, h, w, 64):
+            raise ValueError(f"frames must be [{n * _lib.NUM_FRAMES},{h},{w},64], got {tuple(frames.shape)}")
         out = torch.empty_like(frames)
         check(lib.pfnl_pfrb(self._h, blk, _ptr(frames), n, h, w, _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def conv0(self, inp21):
+        """inp21 [N,H,W,21] (frame t = channels 3t..3t+2) -> conv0 of every frame [N*7,H,W,64] (pfnl.py:48,61-62)."""
+        self._chk_in(inp21, 4)
+        n, h, w, c = inp21.shape
+        if c != 3 * _lib.NUM_FRAMES:
+            raise ValueError("inp21 must be [N,H,W,21]")
+        out = torch.empty((n * _lib.NUM_FRAMES, h, w, 64), dtype=torch.float32, device=self.device)
+        check(lib.pfnl_conv0(self._h, _ptr(inp21), n, h, w, _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def convmerge1(self, frames, n, h, w):
+        """frames [N*7,H,W,64] -> convmerge1 over the concat of the 7 frames [N,H,W,48] (pfnl.py:52,73-74)."""
+        self._chk_in(frames, 4)
+        if tuple(frames.shape) != (n * _lib.NUM_FRAMES, h, w, 64):
+            raise ValueError(f"frames must be [{n * _lib.NUM_FRAMES},{h},{w},64], got {tuple(frames.shape)}")
+        out = torch.empty((n, h, w, 48), dtype=torch.float32, device=self.device)
+        check(lib.pfnl_convmerge1(self._h, _ptr(frames), n, h, w, _ptr(out), _stream_ptr(self.device)))
         return out
 
 

@@ -200,3 +200,95 @@ def test_forward_128_fp16x3(tc_engines):
     y = tc_engines[("fp16x3", "B")].forward(cu(x)).cpu().numpy()
     ref = R.pfnl_forward(x, R.make_weights("B"), backend="torch")
     assert np.abs(y - ref).max() <= 1e-3
+
+
+# ---- the PFRB stack as one persistent dataflow kernel (csrc/pfrb_flow.cu) -----------------------------------
+@pytest.mark.parametrize("prec", ["fp16x3", "fp16"])
+@pytest.mark.parametrize("shape", [(1, 32, 32), (16, 32, 32), (2, 6, 10), (1, 34, 18), (3, 48, 40), (1, 128, 128)])
+def test_flow_matches_phase_kernels(tc_engines, prec, shape):
+    """Same per-tile arithmetic, different scheduling: the dataflow kernel (148 persistent CTAs with one role each,
+    ordered by arrival counters) must reproduce the two-launches-per-block kernels bit for bit - any missed
+    dependency (a tile read before its producer finished) shows up as a difference.  Shapes: fewer tiles than
+    CTAs, the bench shape, ragged borders, several tile rows/columns, config 4."""
+    n, h, w = shape
+    eng = tc_engines[(prec, "A")]
+    x = cu(R.make_input(n, h, w))
+    try:
+        eng.set_flow(False)
+        y_phase = eng.forward(x).clone()
+        eng.set_flow(True)
+        l0 = eng.launches
+        y_flow = eng.forward(x).clone()
+        n_flow = eng.launches - l0
+        y_flow2 = eng.forward(x).clone()  # the counters were cleared by the first launch
+    finally:
+        eng.set_flow(True)
+    torch.cuda.synchronize()
+    # nl_prep, nl_tc, (nl_merge when the keys are split over CTAs,) nl_linear, conv0, pfrb_flow, convmerge1, tail
+    assert n_flow in (7, 8), n_flow
+    assert torch.equal(y_flow, y_phase), float((y_flow - y_phase).abs().max())
+    assert torch.equal(y_flow2, y_phase)
+
+
+def test_flow_repeated_and_shape_changes(tc_engines):
+    """The dependency counters are handle-owned and self-clearing: alternate shapes and repeat."""
+    eng = tc_engines[("fp16x3", "B")]
+    shapes = [(2, 16, 16), (1, 32, 32), (2, 16, 16), (4, 8, 24), (1, 32, 32)]
+    first = {}
+    for n, h, w in shapes * 2:
+        y = eng.forward(cu(R.make_input(n, h, w)))
+        torch.cuda.synchronize()
+        if (n, h, w) in first:
+            assert torch.equal(y, first[(n, h, w)])
+        else:
+            first[(n, h, w)] = y.clone()
+    ref = R.pfnl_forward(R.make_input(1, 32, 32), R.make_weights("B"), dtype=np.float64)
+    assert np.abs(first[(1, 32, 32)].cpu().numpy() - ref).max() <= 1e-3
+
+
+# ---- stage-level parity of the two tcgen05 kernels that were only covered end to end (SURVEY 8a: a5, a8) -------
+@pytest.mark.parametrize("prec,tol", [("fp16x3", 2e-5), ("fp16", 2e-2)])
+@pytest.mark.parametrize("regime", ["A", "B"])
+@pytest.mark.parametrize("shape", [(1, 32, 32), (2, 6, 10), (1, 34, 18), (3, 16, 8)])
+def test_conv0_stage(tc_engines, prec, tol, regime, shape):
+    """conv0 5x5 3->64 + leaky_relu on every frame (pfnl.py:48,61-62) through conv0_tc_kernel (explicit im2col on
+    tcgen05) vs the fp64 oracle; ragged shapes put TMA-free zero padding on every border, negative pre-activations
+    exercise the 0.2 slope."""
+    n, h, w = shape
+    W = R.make_weights(regime)  # regime B has non-zero biases
+    rng = np.random.default_rng(100 + h * 10 + w)
+    inp21 = rng.standard_normal((n, h, w, 21)).astype(np.float32)
+    out = tc_engines[(prec, regime)].conv0(cu(inp21)).cpu().numpy().reshape(n, 7, h, w, 64)
+    k = W["nlvsr/conv0/kernel"].astype(np.float64)
+    b = W["nlvsr/conv0/bias"].astype(np.float64)
+    ref = np.stack([R.conv2d_same(inp21[..., 3 * t:3 * t + 3].astype(np.float64), k, b, act=True)
+                    for t in range(7)], 1)
+    err = np.abs(out - ref)
+    scale = max(1.0, np.abs(ref).max())
+    print(f"{prec} {regime} {shape}: conv0 max-abs {err.max():.3e} (|ref|max {np.abs(ref).max():.2f})")
+    assert (ref < 0).any()
+    assert err.max() <= tol * scale
+    assert err[:, :, [0, 1, -2, -1]].max() <= tol * scale and err[:, :, :, [0, 1, -2, -1]].max() <= tol * scale
+
+
+@pytest.mark.parametrize("prec,tol", [("fp16x3", 2e-5), ("fp16", 2e-2)])
+@pytest.mark.parametrize("regime", ["A", "B"])
+@pytest.mark.parametrize("shape", [(1, 32, 32), (2, 6, 10), (1, 34, 18)])
+def test_convmerge1_stage(tc_engines, prec, tol, regime, shape):
+    """convmerge1 3x3 448->48 + leaky_relu over the concat of the 7 frames (pfnl.py:52,73-74) through the 7-phase
+    tcgen05 launch (N = 48, fp32 partial sums accumulated in place) vs the fp64 oracle.  Regime B has non-zero
+    biases."""
+    n, h, w = shape
+    W = R.make_weights(regime)
+    rng = np.random.default_rng(200 + h * 10 + w)
+    fr = rng.standard_normal((n * 7, h, w, 64)).astype(np.float32)
+    out = tc_engines[(prec, regime)].convmerge1(cu(fr), n, h, w).cpu().numpy()
+    cat = np.concatenate([fr.reshape(n, 7, h, w, 64)[:, t] for t in range(7)], -1).astype(np.float64)
+    ref = R.conv2d_same(cat, W["nlvsr/convmerge1/kernel"].astype(np.float64),
+                        W["nlvsr/convmerge1/bias"].astype(np.float64), act=True)
+    err = np.abs(out - ref)
+    scale = max(1.0, np.abs(ref).max())
+    print(f"{prec} {regime} {shape}: convmerge1 max-abs {err.max():.3e} (|ref|max {np.abs(ref).max():.2f})")
+    assert out.shape == (n, h, w, 48)
+    assert err.max() <= tol * scale
+    assert err[:, [0, -1]].max() <= tol * scale and err[:, :, [0, -1]].max() <= tol * scale
