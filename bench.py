@@ -270,6 +270,29 @@ def run_ours(args):
         eng.forward_host(x_host, out=out_host)
     torch.cuda.synchronize()
 
+    # ---- parity of THIS run's computation on THIS run's inputs (outside every timed region): the first clips of
+    #      the batch the timed loop processes, against the CPU oracle in float64 ("true" value) and in float32
+    #      (what the reference computes in); the 1e-3 gate of BASELINE.json's north_star
+    parity_check = None
+    if rank == 0 and args.parity_clips > 0:
+        from oracle import pfnl_ref as R
+        pc = min(args.parity_clips, clips)
+        eng.forward(x_dev, out=out_dev)
+        torch.cuda.synchronize()
+        got = out_dev[:pc].cpu().numpy()
+        xin = x_host[:pc].numpy()
+        Wd = WT.xavier_init()
+        ref64 = R.pfnl_forward(xin, Wd, dtype=np.float64, backend="torch")
+        ref32 = R.pfnl_forward(xin, Wd, dtype=np.float32, backend="numpy")
+        e64 = float(np.abs(got - ref64).max())
+        e32 = float(np.abs(got - ref32).max())
+        parity_check = {"clips_checked": pc, "of_batch": clips, "max_abs_vs_fp64_oracle": e64,
+                        "max_abs_vs_fp32_oracle": e32, "oracle_fp32_vs_fp64": float(np.abs(ref32 - ref64).max()),
+                        "output_abs_max": float(np.abs(ref64).max()), "gate": 1e-3,
+                        "ok": bool(e64 <= 1e-3 and e32 <= 1e-3) if args.precision != "fp16" else None,
+                        "what": "rows of the timed batch's output vs oracle/pfnl_ref.py on the same rows (regime A "
+                                "= the reference's own Xavier initialisation, outputs reach +-100)"}
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -293,17 +316,88 @@ def run_ours(args):
     step_ms = [a.elapsed_time(b) for a, b in evs]
     ms_dev = D.max_over_ranks(sum(step_ms) / K, device=dev)
 
-    # ---- end to end through the public API with host buffers --------------------------------------
-    e2e_times = []
-    barrier()
-    for _ in range(K):
-        flush.zero_()
+    # ---- end to end through the public API with HOST buffers --------------------------------------------
+    # (a) blocking calls: H2D -> forward -> D2H, one batch at a time (pfnl_forward_host)
+    # (b) the same feed/fetch pipelined over consecutive batches (pfnl_forward_host_submit/_wait, two staging slots):
+    #     every step still copies its own input up and its own result down, the copies of neighbouring steps run
+    #     under the forward.  Timed region = first submit .. last wait, host clock, max over ranks.
+    # (c) both again with a pageable float64 numpy input, which is what the reference's call site feeds
+    #     (model/pfnl.py:209,252); the library narrows it on its way into pinned staging.
+    out_host2 = torch.empty_like(out_host).pin_memory()
+    x_np64 = x_host.numpy().astype(np.float64)            # pageable
+    out_np = torch.empty_like(out_host)                     # pageable destination
+
+    def e2e_sync(inp, out):
+        ts = []
+        for _ in range(K):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            eng.forward_host(inp, out=out)
+            ts.append(time.perf_counter() - t0)
+        return 1e3 * sum(ts) / K
+
+    def e2e_pipelined(inp, outs):
+        eng.forward_host(inp, out=outs[0])
         torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
-        eng.forward_host(x_host, out=out_host)   # H2D (pinned) + forward + D2H, returns when out_host is complete
-        e2e_times.append(time.perf_counter() - t0)
+        prev = None
+        for k in range(K):
+            tk, _ = eng.forward_host_submit(inp, out=outs[k % 2])
+            if prev is not None:
+                eng.forward_host_wait(prev)
+            prev = tk
+        eng.forward_host_wait(prev)
+        return 1e3 * (time.perf_counter() - t0) / K
+
     barrier()
-    ms_e2e = D.max_over_ranks(1e3 * sum(e2e_times) / K, device=dev)
+    ms_e2e_sync = D.max_over_ranks(e2e_sync(x_host, out_host), device=dev)
+    ms_e2e = D.max_over_ranks(e2e_pipelined(x_host, [out_host, out_host2]), device=dev)
+    ms_e2e_f64_sync = D.max_over_ranks(e2e_sync(x_np64, out_np), device=dev)
+    ms_e2e_f64 = D.max_over_ranks(e2e_pipelined(x_np64, [out_np, torch.empty_like(out_np)]), device=dev)
+    barrier()
+
+    # ---- the step with its collective (BASELINE configs[2]: per-clip MSE all-gathered for the PSNR reduction,
+    #      model/pfnl.py:90,139-141): forward -> pfnl_mse -> NCCL all-gather of the [clips] vector ------------
+    hr_dev = torch.rand((clips, 1, 4 * size, 4 * size, 3), generator=torch.Generator().manual_seed(1235 + rank),
+                        dtype=torch.float32).to(dev)
+    gathered = torch.empty((world * clips,), dtype=torch.float32, device=dev)
+
+    def step_with_collective():
+        eng.forward(x_dev, out=out_dev)
+        mse = eng.mse(out_dev, hr_dev)
+        if world > 1:
+            torch.distributed.all_gather_into_tensor(gathered, mse)
+        else:
+            gathered.copy_(mse)
+
+    for _ in range(3):
+        step_with_collective()
+    torch.cuda.synchronize()
+    evc = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    for a, b in evc:
+        flush.zero_()
+        a.record()
+        step_with_collective()
+        b.record()
+    torch.cuda.synchronize()
+    ms_coll_step = D.max_over_ranks(sum(a.elapsed_time(b) for a, b in evc) / K, device=dev)
+    # the collective alone (latency-bound: clips x 4 bytes per rank)
+    mse_fixed = eng.mse(out_dev, hr_dev)
+    evg = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    for a, b in evg:
+        a.record()
+        if world > 1:
+            torch.distributed.all_gather_into_tensor(gathered, mse_fixed)
+        else:
+            gathered.copy_(mse_fixed)
+        b.record()
+    torch.cuda.synchronize()
+    us_gather = 1e3 * D.max_over_ranks(sum(a.elapsed_time(b) for a, b in evg) / K, device=dev)
+    psnr_mean = float((10.0 * torch.log10(1.0 / gathered.double())).mean().item())
 
     # ---- per-kernel-class timing for the roofline (same workload, K steps) -----------------------
     eng.profile(True)
@@ -313,6 +407,55 @@ def run_ours(args):
     prof = eng.profile_read()
     eng.profile(False)
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- non-local block in isolation at L = 4096 (BASELINE configs[3]/[4]): FLOP roofline of the kernel the
+    #      headline precision ships (the 32x32 clips of the timed workload have L = 256: 22 MFLOP of MMA per clip,
+    #      latency-bound - quoting a fraction there would say nothing)
+    nl_roof = None
+    if rank == 0 and world == 1 and args.precision != "fp32" and not args.no_nl_roofline:
+        peaks_ = load_peaks()
+        nl_roof = {"L": 4096, "channels": 84, "precision": args.precision, "peak_tflops_burst": peaks_["tensor_tflops_burst"],
+                   "peak_source": peaks_["source"], "cases": []}
+        try:
+            for ncl in (1, 4):
+                tok = torch.rand((ncl, 4096, 84), generator=torch.Generator().manual_seed(99), dtype=torch.float32).to(dev)
+                for _ in range(3):
+                    eng.nonlocal_block(tok)
+                torch.cuda.synchronize()
+                eng.profile(True)
+                evn = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+                for a, b in evn:
+                    flush.zero_()
+                    a.record()
+                    eng.nonlocal_block(tok)
+                    b.record()
+                torch.cuda.synchronize()
+                pr = eng.profile_read()
+                eng.profile(False)
+                blk_ms = sum(a.elapsed_time(b) for a, b in evn) / len(evn)
+                k_ms = pr["nl_tc_kernel"][0] / max(pr["nl_tc_kernel"][1], 1)
+                f_l2 = ncl * 4.0 * 84 * 4096 * 4096            # the two L^2 contractions (useful FLOPs)
+                f_blk = ncl * 4.0 * 84 * 4096 * (84 + 4096)    # + the two 1x1 convs, as the reference computes them
+                split = args.precision == "fp16x3"
+                # executed tensor FLOPs per useful one: fp16x3 runs 3 products for S and 2 for PV (operands padded
+                # 84 -> 128 / 96 are not counted)
+                exec_factor = 2.5 if split else 1.0
+                nl_roof["cases"].append({
+                    "clips": ncl, "block_ms": blk_ms, "kernel_ms": k_ms,
+                    "block_tflops": f_blk / blk_ms / 1e9, "kernel_tflops_useful": f_l2 / k_ms / 1e9,
+                    "kernel_frac_of_burst_peak_useful": f_l2 / k_ms / 1e9 / peaks_["tensor_tflops_burst"],
+                    "kernel_tflops_executed": exec_factor * f_l2 / k_ms / 1e9,
+                    "kernel_frac_of_burst_peak_executed": exec_factor * f_l2 / k_ms / 1e9 / peaks_["tensor_tflops_burst"]})
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+                nl_roof["ncu_tensor_pipe_pct"] = tj.get(args.precision, {}).get("nl_tc_kernel_tensor_pipe_pct")
+            except Exception:
+                nl_roof["ncu_tensor_pipe_pct"] = None
+            nl_roof["how"] = ("pfnl_nonlocal (stage entry: nl_prep + nl_tc_kernel [+ key-split merge] + output linear) "
+                              "timed with CUDA events, 10 iterations, L2 flushed; kernel_ms = nl_tc_kernel alone "
+                              "(pfnl_profile events); useful FLOPs = 4*84*L^2 per clip")
+        except Exception as ex:
+            nl_roof["error"] = str(ex)[:200]
 
     if rank != 0:
         return 0
@@ -376,9 +519,9 @@ def run_ours(args):
     if args.precision.startswith("fp16x3"):
         roofline["tensor_executed_tflops"] = 3.0 * tfl
         roofline["note"] = ("fp16x3 executes 3 tensor FLOPs per useful FLOP (hi*hi, hi*lo, lo*hi); 'achieved' counts "
-                            "useful FLOPs only. Measured tcgen05 law on this part (profiles/r1_mma_rate_probe.txt): "
-                            "cycles/MMA = max(N/2,40)+21.6 at M=128,K=16, i.e. a Cout=64 conv tops out at ~65% of "
-                            "nominal tensor peak in this mode")
+                            "useful FLOPs only. Measured tcgen05 law on this part (profiles/r2a_mma_rate_probe.txt): "
+                            "cycles/MMA = 37.6+0.375N (N<=128) at M=128,K=16, the same per SM for cta_group::2 pairs, "
+                            "i.e. a Cout=64 conv tops out at ~65% of nominal tensor peak in this mode")
     if not tc:
         roofline["note"] =("fp32 parity path: this kernel is FFMA-bound (%.1f TFLOP/s fp32 on CUDA cores), "
                             "not HBM-bound" % tfl)
@@ -402,11 +545,33 @@ def run_ours(args):
                    "timing": "per-step CUDA events on the launching stream, mean over K, max over ranks"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4),
-                "how": "pfnl_forward_host via Engine.forward_host: pinned host LR -> device, forward, SR -> pinned host"},
+                "how": "Engine.forward_host_submit/_wait (pfnl_forward_host_submit/_wait): every step copies its "
+                       "pinned float32 LR batch to the device, runs the forward and copies its SR batch back to "
+                       "pinned host memory; two batches in flight, so a step's copies run under its neighbours' "
+                       "forwards; host clock from the first submit to the last wait, max over ranks",
+                "blocking_call_ms_per_step": ms_e2e_sync,
+                "blocking_call_value": total_clips * HR_PX_PER_CLIP(size, size) / (ms_e2e_sync / 1e3),
+                "pageable_float64_input": {
+                    "what": "the reference's own feed: a pageable float64 numpy batch (model/pfnl.py:209,252) and a "
+                            "pageable float32 result; narrowed to float32 on its way into pinned staging",
+                    "ms_per_step": ms_e2e_f64, "value": total_clips * HR_PX_PER_CLIP(size, size) / (ms_e2e_f64 / 1e3),
+                    "blocking_call_ms_per_step": ms_e2e_f64_sync,
+                    "h2d_bytes_per_step": int(x_host.numel() * 4), "host_bytes_read_per_step": int(x_host.numel() * 8)},
+                "e2e_over_device_ms": ms_e2e / ms_dev},
+        "with_collective": {
+            "what": "the same step followed by pfnl_mse and the all-gather of the per-clip MSE vector over all ranks "
+                    "(model/pfnl.py:90,139-141; NCCL over NVLink at N > 1, a device copy at N = 1), CUDA events on the "
+                    "launching stream, max over ranks",
+            "ms_per_step": ms_coll_step,
+            "value": total_clips * HR_PX_PER_CLIP(size, size) / (ms_coll_step / 1e3), "unit": UNIT,
+            "collective_us": us_gather, "collective_bytes_per_rank": clips * 4,
+            "backend": "nccl" if world > 1 else "none (1 rank)", "mean_psnr_db_vs_random_target": psnr_mean},
         "gpu_launches": int(launches),
         "launches_per_step": launches / K,
         "wall_s_timed_region": wall_total,
         "roofline": roofline,
+        "nonlocal_roofline": nl_roof,
+        "parity_check": parity_check,
         "kernel_ms_per_step": {k: v[0] / K for k, v in prof.items() if v[1]},
         "clocks": clocks,
     }
@@ -469,6 +634,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the short passes of the other precisions")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--parity-clips", type=int, default=2,
+                    help="clips of the timed batch checked against the CPU oracle (fp64 + fp32) outside the timed region")
+    ap.add_argument("--no-nl-roofline", action="store_true", help="skip the L=4096 non-local isolation pass")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -104,7 +104,9 @@ size_t pfnl_workspace_bytes(int precision, int N, int H, int W);
 /* Pre-allocates the workspace for (N,H,W) so that pfnl_forward does not allocate
  * (and can be captured in a CUDA graph).  Synchronous. */
 int pfnl_reserve(pfnl_handle* h, int N, int H, int W);
-/* 1: pfnl_forward replays a cached CUDA graph per (N,H,W) shape; 0: plain launches. */
+/* 1: pfnl_forward replays a cached CUDA graph per (N,H,W) shape and buffer pair (a new buffer pair of a known shape
+ * re-points an existing executable instead of instantiating again; the legacy NULL stream is served through a
+ * private stream ordered with events); 0: plain launches. */
 int pfnl_set_graphs(pfnl_handle* h, int enable);
 /* Tensor-core precisions only.  1 (default): the 20 PFRBs (model/pfnl.py:65-71) run as ONE persistent dataflow
  * kernel (csrc/pfrb_flow.cu); 0: two launches per block (csrc/conv_tc.cu).  Same arithmetic, bit-identical
@@ -129,6 +131,19 @@ int pfnl_forward(pfnl_handle* h, const float* lr_dev, int N, int H, int W, float
  * returns when sr_host is complete. */
 int pfnl_forward_host(pfnl_handle* h, const float* lr_host, int N, int H, int W, float* sr_host,
                       void* stream);
+/* The same feed/fetch, pipelined over consecutive batches (the loop of test_video_*, model/pfnl.py:246-253): submit
+ * copies lr to the device on a copy stream, runs the forward on `stream` and starts the copy of sr back on another
+ * copy stream, then returns a ticket (0 or 1: two staging slots); wait(ticket) returns when that call's sr_host is
+ * complete.  Submitting batch k+1 before waiting for batch k overlaps its H2D (and the D2H of batch k) with compute.
+ * A submit first waits for the call that used its slot two submits earlier.  lr_dtype 0: float32, 1: float64 (the
+ * reference feeds float64 numpy arrays into its float32 placeholder, model/pfnl.py:209,252) - narrowed on the way
+ * into pinned staging.  Pinned float32 inputs / pinned outputs are copied directly. */
+int pfnl_forward_host_submit(pfnl_handle* h, const void* lr_host, int lr_dtype, int N, int H, int W, float* sr_host,
+                             void* stream, int* ticket);
+int pfnl_forward_host_wait(pfnl_handle* h, int ticket);
+/* CUDA-graph cache counters: what = 0 executables instantiated, 1 executables re-pointed in place
+ * (cudaGraphExecUpdate), 2 executables currently cached. */
+long long pfnl_graph_stats(const pfnl_handle* h, int what);
 
 /* Replaces: eval_mse = tf.reduce_mean((SR-H)**2, axis=[2,3,4]), model/pfnl.py:90.
  *   sr_dev, hr_dev [N,1,H4,W4,3] -> mse_dev [N]. */

@@ -63,6 +63,9 @@ SYMBOLS = {
     "pfnl_debug_progress": (_I, [C.POINTER(C.c_int), _I]),
     "pfnl_forward": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
     "pfnl_forward_host": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
+    "pfnl_forward_host_submit": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _VP, C.POINTER(_I)]),
+    "pfnl_forward_host_wait": (_I, [_VP, _I]),
+    "pfnl_graph_stats": (C.c_longlong, [_VP, _I]),
     "pfnl_mse": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP, _VP]),
     "pfnl_launch_count": (C.c_longlong, [_VP]),
     "pfnl_profile": (_I, [_VP, _I]),

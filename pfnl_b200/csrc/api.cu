@@ -135,14 +135,37 @@ struct pfnl_handle {
   float* pack_scratch = nullptr;
   size_t pack_cap = 0;
   float* blur_dev = nullptr;  // 13x13 taps of pfnl_downsample4
-  // host staging for pfnl_forward_host
-  float *pin_in = nullptr, *pin_out = nullptr, *dev_in = nullptr, *dev_out = nullptr;
-  size_t pin_in_cap = 0, pin_out_cap = 0;
+  // host staging of pfnl_forward_host[_submit]: two slots so that the H2D copy of call k+1 and the D2H copy of
+  // call k-1 run (on their own streams) under the forward of call k
+  struct HostSlot {
+    float *pin_in = nullptr, *pin_out = nullptr, *dev_in = nullptr, *dev_out = nullptr;
+    size_t in_cap = 0, out_cap = 0;
+    cudaEvent_t in_ready = nullptr, fwd_done = nullptr, out_ready = nullptr;
+    bool busy = false;        // submitted, not yet waited for
+    float* user_out = nullptr;  // pageable destination to fill from pin_out at wait time (NULL: copied directly)
+    size_t out_bytes = 0;
+  } slot[2];
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  int next_slot = 0;
   long long launches = 0;
   Profiler prof;
   bool graphs = false;
-  std::map<std::tuple<int, int, int, const void*, void*>, cudaGraphExec_t> graph_cache;
-  std::map<std::tuple<int, int, int, const void*, void*>, long long> graph_nodes;
+  // CUDA-graph cache of the forward launch sequence, keyed by shape and buffer addresses; a miss for a known
+  // shape recycles the least recently used executable of that shape with cudaGraphExecUpdate (same topology,
+  // new pointers) instead of instantiating again
+  struct GraphEntry {
+    int N, H, W;
+    const void* lr;
+    void* sr;
+    cudaGraphExec_t exec;
+    long long nodes;
+    unsigned long long stamp;
+  };
+  std::vector<GraphEntry> graph_cache;
+  unsigned long long graph_clock = 0;
+  long long graph_instantiations = 0, graph_updates = 0;
+  cudaStream_t graph_stream = nullptr;  // stands in for the legacy NULL stream, which cannot be captured
+  cudaEvent_t graph_ev_in = nullptr, graph_ev_out = nullptr;
 };
 
 namespace {
@@ -221,9 +244,8 @@ int ensure_workspace(pfnl_handle* h, int N, int H, int W) {
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
   if (h->ws) {
     PFNL_CUDA(cudaDeviceSynchronize());
-    for (auto& kv : h->graph_cache) cudaGraphExecDestroy(kv.second);
+    for (auto& e : h->graph_cache) cudaGraphExecDestroy(e.exec);
     h->graph_cache.clear();
-    h->graph_nodes.clear();
     PFNL_CUDA(cudaFree(h->ws));
     h->ws = nullptr;
     h->ws_cap = 0;
@@ -407,6 +429,7 @@ int pfnl_create(pfnl_handle** out, int device, const pfnl_weights* wts, int prec
   do {                      \
     if ((rc = (x))) goto fail; \
   } while (0)
+  tc_fault_buffer();  // allocate the host-mapped fault record now: not allowed later inside a stream capture
   TRY(init_conv_ffma());
   TRY(init_nonlocal_ffma());
   TRY(init_metrics());
@@ -502,7 +525,21 @@ int pfnl_destroy(pfnl_handle* h) {
   if (!h) return PFNL_OK;
   DeviceGuard guard(h->device);
   cudaDeviceSynchronize();
-  for (auto& kv : h->graph_cache) cudaGraphExecDestroy(kv.second);
+  for (auto& e : h->graph_cache) cudaGraphExecDestroy(e.exec);
+  if (h->graph_stream) cudaStreamDestroy(h->graph_stream);
+  if (h->graph_ev_in) cudaEventDestroy(h->graph_ev_in);
+  if (h->graph_ev_out) cudaEventDestroy(h->graph_ev_out);
+  for (auto& sl : h->slot) {
+    if (sl.pin_in) cudaFreeHost(sl.pin_in);
+    if (sl.pin_out) cudaFreeHost(sl.pin_out);
+    if (sl.dev_in) cudaFree(sl.dev_in);
+    if (sl.dev_out) cudaFree(sl.dev_out);
+    if (sl.in_ready) cudaEventDestroy(sl.in_ready);
+    if (sl.fwd_done) cudaEventDestroy(sl.fwd_done);
+    if (sl.out_ready) cudaEventDestroy(sl.out_ready);
+  }
+  if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+  if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
   for (auto& r : h->prof.recs) {
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
@@ -516,10 +553,6 @@ int pfnl_destroy(pfnl_handle* h) {
   if (h->metric_buf) cudaFree(h->metric_buf);
   if (h->pack_scratch) cudaFree(h->pack_scratch);
   if (h->blur_dev) cudaFree(h->blur_dev);
-  if (h->pin_in) cudaFreeHost(h->pin_in);
-  if (h->pin_out) cudaFreeHost(h->pin_out);
-  if (h->dev_in) cudaFree(h->dev_in);
-  if (h->dev_out) cudaFree(h->dev_out);
   cudaGetLastError();
   delete h;
   return PFNL_OK;
@@ -558,9 +591,8 @@ int pfnl_set_flow(pfnl_handle* h, int enable) {
   if ((enable != 0) != h->tcw.flow) {  // captured graphs hold the other launch sequence
     DeviceGuard guard(h->device);
     PFNL_CUDA(cudaDeviceSynchronize());
-    for (auto& kv : h->graph_cache) cudaGraphExecDestroy(kv.second);
+    for (auto& e : h->graph_cache) cudaGraphExecDestroy(e.exec);
     h->graph_cache.clear();
-    h->graph_nodes.clear();
   }
   h->tcw.flow = enable != 0;
   return PFNL_OK;
@@ -633,17 +665,34 @@ int pfnl_forward(pfnl_handle* h, const float* lr, int N, int H, int W, float* sr
     set_error("pfnl_forward: stream is capturing and the workspace for (%d,%d,%d) is not reserved", N, H, W);
     return PFNL_ERR_BAD_ARG;
   }
-  if (!h->graphs || h->prof.on || cap != cudaStreamCaptureStatusNone || s == nullptr)
-    return forward_launches(h, lr, N, H, W, sr, s);
+  if (!h->graphs || h->prof.on || cap != cudaStreamCaptureStatusNone) return forward_launches(h, lr, N, H, W, sr, s);
 
-  auto key = std::make_tuple(N, H, W, (const void*)lr, (void*)sr);
-  auto it = h->graph_cache.find(key);
-  if (it == h->graph_cache.end()) {
+  // The legacy NULL stream cannot be captured: run the graph on a private stream ordered after / before the
+  // caller's stream with two events.
+  cudaStream_t gs = s;
+  if (s == nullptr) {
+    if (!h->graph_stream) {
+      PFNL_CUDA(cudaStreamCreateWithFlags(&h->graph_stream, cudaStreamNonBlocking));
+      PFNL_CUDA(cudaEventCreateWithFlags(&h->graph_ev_in, cudaEventDisableTiming));
+      PFNL_CUDA(cudaEventCreateWithFlags(&h->graph_ev_out, cudaEventDisableTiming));
+    }
+    gs = h->graph_stream;
+  }
+  pfnl_handle::GraphEntry* hit = nullptr;
+  pfnl_handle::GraphEntry* recycle = nullptr;  // least recently used executable of the same shape
+  int same_shape = 0;
+  for (auto& e : h->graph_cache) {
+    if (e.N != N || e.H != H || e.W != W) continue;
+    ++same_shape;
+    if (e.lr == (const void*)lr && e.sr == (void*)sr) hit = &e;
+    if (!recycle || e.stamp < recycle->stamp) recycle = &e;
+  }
+  if (!hit) {
     cudaGraph_t graph = nullptr;
     const long long before = h->launches;
-    PFNL_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    rc = forward_launches(h, lr, N, H, W, sr, s);
-    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    PFNL_CUDA(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+    rc = forward_launches(h, lr, N, H, W, sr, gs);
+    cudaError_t e = cudaStreamEndCapture(gs, &graph);
     const long long nodes = h->launches - before;
     h->launches = before;
     if (rc) {
@@ -651,20 +700,157 @@ int pfnl_forward(pfnl_handle* h, const float* lr, int N, int H, int W, float* sr
       return rc;
     }
     if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
-    cudaGraphExec_t exec = nullptr;
-    e = cudaGraphInstantiate(&exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
-    if (h->graph_cache.size() >= 16) {
-      for (auto& kv : h->graph_cache) cudaGraphExecDestroy(kv.second);
-      h->graph_cache.clear();
-      h->graph_nodes.clear();
+    // callers that alternate between a few buffers (the two slots of pfnl_forward_host, ping-pong outputs) keep
+    // one executable per address pair; beyond 4 per shape the oldest one is re-pointed in place
+    if (same_shape >= 4 && recycle != nullptr) {
+      cudaGraphExecUpdateResultInfo info;
+      if (cudaGraphExecUpdate(recycle->exec, graph, &info) == cudaSuccess) {
+        recycle->lr = lr;
+        recycle->sr = sr;
+        recycle->nodes = nodes;
+        hit = recycle;
+        ++h->graph_updates;
+      } else {
+        cudaGetLastError();
+      }
     }
-    it = h->graph_cache.emplace(key, exec).first;
-    h->graph_nodes[key] = nodes;
+    if (!hit) {
+      cudaGraphExec_t exec = nullptr;
+      e = cudaGraphInstantiate(&exec, graph, 0);
+      if (e != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+      }
+      ++h->graph_instantiations;
+      if (h->graph_cache.size() >= 32) {  // many shapes: drop the globally oldest
+        size_t o = 0;
+        for (size_t i = 1; i < h->graph_cache.size(); ++i)
+          if (h->graph_cache[i].stamp < h->graph_cache[o].stamp) o = i;
+        cudaGraphExecDestroy(h->graph_cache[o].exec);
+        h->graph_cache.erase(h->graph_cache.begin() + o);
+      }
+      h->graph_cache.push_back({N, H, W, lr, sr, exec, nodes, 0});
+      hit = &h->graph_cache.back();
+    }
+    cudaGraphDestroy(graph);
   }
-  PFNL_CUDA(cudaGraphLaunch(it->second, s));
-  h->launches += h->graph_nodes[key];
+  hit->stamp = ++h->graph_clock;
+  if (s == nullptr) {
+    PFNL_CUDA(cudaEventRecord(h->graph_ev_in, s));
+    PFNL_CUDA(cudaStreamWaitEvent(gs, h->graph_ev_in, 0));
+  }
+  PFNL_CUDA(cudaGraphLaunch(hit->exec, gs));
+  if (s == nullptr) {
+    PFNL_CUDA(cudaEventRecord(h->graph_ev_out, gs));
+    PFNL_CUDA(cudaStreamWaitEvent(s, h->graph_ev_out, 0));
+  }
+  h->launches += hit->nodes;
+  return PFNL_OK;
+}
+
+long long pfnl_graph_stats(const pfnl_handle* h, int what) {
+  if (!h) return -1;
+  return what == 0 ? h->graph_instantiations : (what == 1 ? h->graph_updates : (long long)h->graph_cache.size());
+}
+
+// Staging slot `k` sized for (in_bytes, out_bytes).
+static int host_slot_prepare(pfnl_handle* h, int k, size_t in_bytes, size_t out_bytes) {
+  pfnl_handle::HostSlot& sl = h->slot[k];
+  if (!h->h2d_stream) {
+    PFNL_CUDA(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+    PFNL_CUDA(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+  }
+  if (!sl.in_ready) {
+    PFNL_CUDA(cudaEventCreateWithFlags(&sl.in_ready, cudaEventDisableTiming));
+    PFNL_CUDA(cudaEventCreateWithFlags(&sl.fwd_done, cudaEventDisableTiming));
+    PFNL_CUDA(cudaEventCreateWithFlags(&sl.out_ready, cudaEventDisableTiming));
+  }
+  if (in_bytes > sl.in_cap) {
+    if (sl.pin_in) cudaFreeHost(sl.pin_in);
+    if (sl.dev_in) cudaFree(sl.dev_in);
+    sl.pin_in = nullptr;
+    sl.dev_in = nullptr;
+    sl.in_cap = 0;
+    PFNL_CUDA(cudaMallocHost((void**)&sl.pin_in, in_bytes));
+    PFNL_CUDA(cudaMalloc((void**)&sl.dev_in, in_bytes));
+    sl.in_cap = in_bytes;
+  }
+  if (out_bytes > sl.out_cap) {
+    if (sl.pin_out) cudaFreeHost(sl.pin_out);
+    if (sl.dev_out) cudaFree(sl.dev_out);
+    sl.pin_out = nullptr;
+    sl.dev_out = nullptr;
+    sl.out_cap = 0;
+    PFNL_CUDA(cudaMallocHost((void**)&sl.pin_out, out_bytes));
+    PFNL_CUDA(cudaMalloc((void**)&sl.dev_out, out_bytes));
+    sl.out_cap = out_bytes;
+  }
+  return PFNL_OK;
+}
+
+int pfnl_forward_host_wait(pfnl_handle* h, int ticket) {
+  if (!h || ticket < 0 || ticket > 1) {
+    set_error("pfnl_forward_host_wait: bad argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  pfnl_handle::HostSlot& sl = h->slot[ticket];
+  if (!sl.busy) return PFNL_OK;
+  DeviceGuard guard(h->device);
+  PFNL_CUDA(cudaEventSynchronize(sl.out_ready));
+  if (sl.user_out) memcpy(sl.user_out, sl.pin_out, sl.out_bytes);
+  sl.busy = false;
+  sl.user_out = nullptr;
+  return PFNL_OK;
+}
+
+int pfnl_forward_host_submit(pfnl_handle* h, const void* lr_host, int lr_dtype, int N, int H, int W, float* sr_host,
+                             void* stream, int* ticket) {
+  if (!h || !lr_host || !sr_host || !ticket || (lr_dtype != 0 && lr_dtype != 1)) {
+    set_error("pfnl_forward_host_submit: bad argument");
+    return PFNL_ERR_BAD_ARG;
+  }
+  int rc = check_shape(N, H, W);
+  if (rc) return rc;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n_in = (size_t)N * kFrames * H * W * 3;
+  const size_t in_bytes = n_in * sizeof(float);
+  const size_t out_bytes = (size_t)N * 16 * H * W * 3 * sizeof(float);
+  const int k = h->next_slot;
+  if ((rc = pfnl_forward_host_wait(h, k))) return rc;  // the slot's previous call (two submits ago)
+  if ((rc = host_slot_prepare(h, k, in_bytes, out_bytes))) return rc;
+  if ((rc = ensure_workspace(h, N, H, W))) return rc;
+  pfnl_handle::HostSlot& sl = h->slot[k];
+  // A registered (pinned) float32 caller buffer is copied directly; pageable memory goes through the slot's
+  // pinned staging, float64 input (what the reference feeds, model/pfnl.py:209,252) is narrowed on the way in.
+  cudaPointerAttributes at;
+  const bool in_pinned = lr_dtype == 0 && cudaPointerGetAttributes(&at, lr_host) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  const bool out_pinned = cudaPointerGetAttributes(&at, sr_host) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  const float* src = (const float*)lr_host;
+  if (!in_pinned) {
+    if (lr_dtype == 1) {
+      const double* d = (const double*)lr_host;
+      for (size_t i = 0; i < n_in; ++i) sl.pin_in[i] = (float)d[i];
+    } else {
+      memcpy(sl.pin_in, lr_host, in_bytes);
+    }
+    src = sl.pin_in;
+  }
+  PFNL_CUDA(cudaMemcpyAsync(sl.dev_in, src, in_bytes, cudaMemcpyHostToDevice, h->h2d_stream));
+  PFNL_CUDA(cudaEventRecord(sl.in_ready, h->h2d_stream));
+  PFNL_CUDA(cudaStreamWaitEvent(s, sl.in_ready, 0));
+  if ((rc = pfnl_forward(h, sl.dev_in, N, H, W, sl.dev_out, stream))) return rc;
+  PFNL_CUDA(cudaEventRecord(sl.fwd_done, s));
+  PFNL_CUDA(cudaStreamWaitEvent(h->d2h_stream, sl.fwd_done, 0));
+  PFNL_CUDA(cudaMemcpyAsync(out_pinned ? sr_host : sl.pin_out, sl.dev_out, out_bytes, cudaMemcpyDeviceToHost,
+                            h->d2h_stream));
+  PFNL_CUDA(cudaEventRecord(sl.out_ready, h->d2h_stream));
+  sl.busy = true;
+  sl.user_out = out_pinned ? nullptr : sr_host;
+  sl.out_bytes = out_bytes;
+  h->next_slot = k ^ 1;
+  *ticket = k;
   return PFNL_OK;
 }
 
@@ -673,49 +859,10 @@ int pfnl_forward_host(pfnl_handle* h, const float* lr_host, int N, int H, int W,
     set_error("pfnl_forward_host: NULL argument");
     return PFNL_ERR_BAD_ARG;
   }
-  int rc = check_shape(N, H, W);
+  int ticket = -1;
+  int rc = pfnl_forward_host_submit(h, lr_host, 0, N, H, W, sr_host, stream, &ticket);
   if (rc) return rc;
-  DeviceGuard guard(h->device);
-  cudaStream_t s = (cudaStream_t)stream;
-  const size_t in_bytes = (size_t)N * kFrames * H * W * 3 * sizeof(float);
-  const size_t out_bytes = (size_t)N * 16 * H * W * 3 * sizeof(float);
-  if (in_bytes > h->pin_in_cap) {
-    if (h->pin_in) cudaFreeHost(h->pin_in);
-    if (h->dev_in) cudaFree(h->dev_in);
-    h->pin_in = nullptr;
-    h->dev_in = nullptr;
-    h->pin_in_cap = 0;
-    PFNL_CUDA(cudaMallocHost((void**)&h->pin_in, in_bytes));
-    PFNL_CUDA(cudaMalloc((void**)&h->dev_in, in_bytes));
-    h->pin_in_cap = in_bytes;
-  }
-  if (out_bytes > h->pin_out_cap) {
-    if (h->pin_out) cudaFreeHost(h->pin_out);
-    if (h->dev_out) cudaFree(h->dev_out);
-    h->pin_out = nullptr;
-    h->dev_out = nullptr;
-    h->pin_out_cap = 0;
-    PFNL_CUDA(cudaMallocHost((void**)&h->pin_out, out_bytes));
-    PFNL_CUDA(cudaMalloc((void**)&h->dev_out, out_bytes));
-    h->pin_out_cap = out_bytes;
-  }
-  // A registered (pinned) caller buffer is copied directly; pageable memory goes through staging.
-  cudaPointerAttributes at;
-  const bool in_pinned = cudaPointerGetAttributes(&at, lr_host) == cudaSuccess && at.type == cudaMemoryTypeHost;
-  const bool out_pinned = cudaPointerGetAttributes(&at, sr_host) == cudaSuccess && at.type == cudaMemoryTypeHost;
-  cudaGetLastError();
-  const float* src = lr_host;
-  if (!in_pinned) {
-    memcpy(h->pin_in, lr_host, in_bytes);
-    src = h->pin_in;
-  }
-  PFNL_CUDA(cudaMemcpyAsync(h->dev_in, src, in_bytes, cudaMemcpyHostToDevice, s));
-  if ((rc = pfnl_forward(h, h->dev_in, N, H, W, h->dev_out, stream))) return rc;
-  float* dst = out_pinned ? sr_host : h->pin_out;
-  PFNL_CUDA(cudaMemcpyAsync(dst, h->dev_out, out_bytes, cudaMemcpyDeviceToHost, s));
-  PFNL_CUDA(cudaStreamSynchronize(s));
-  if (!out_pinned) memcpy(sr_host, h->pin_out, out_bytes);
-  return PFNL_OK;
+  return pfnl_forward_host_wait(h, ticket);
 }
 
 int pfnl_mse(pfnl_handle* h, const float* sr, const float* hr, int N, int H4, int W4, float* mse, void* stream) {
@@ -768,7 +915,7 @@ int pfnl_nonlocal(pfnl_handle* h, const float* tokens, int N, int L, float* out,
   }
   DeviceGuard guard(h->device);
   cudaStream_t s = (cudaStream_t)stream;
-  if (tc_nl_on_tensor_cores(h->precision) && tc_has_nonlocal()) return tc_nonlocal_tokens(h->tcw, tokens, N, L, out, s, &h->launches);
+  if (tc_nl_on_tensor_cores(h->precision) && tc_has_nonlocal()) return tc_nonlocal_tokens(h->tcw, tokens, N, L, out, s, &h->launches, h->prof.on ? &h->prof : nullptr);
   // scratch: G and Y live in the workspace sized for an equivalent (N, 2, 2L) frame
   int rc = ensure_workspace(h, N, 2, 2 * L);
   if (rc) return rc;
@@ -1073,18 +1220,20 @@ int pfnl_ssim_y(pfnl_handle* h, const float* a, const float* b, int F, int H, in
 
 // Table-driven CRC-32C, 8 bytes per step (slicing-by-8); host only.
 uint32_t pfnl_crc32c(const void* data, size_t n, uint32_t crc) {
-  static uint32_t tab[8][256];
-  static bool ready = false;
-  if (!ready) {
-    for (uint32_t i = 0; i < 256; ++i) {
-      uint32_t c = i;
-      for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? 0x82F63B78u : 0u);
-      tab[0][i] = c;
+  struct Table {
+    uint32_t t[8][256];
+    Table() {
+      for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? 0x82F63B78u : 0u);
+        t[0][i] = c;
+      }
+      for (uint32_t i = 0; i < 256; ++i)
+        for (int k = 1; k < 8; ++k) t[k][i] = (t[k - 1][i] >> 8) ^ t[0][t[k - 1][i] & 0xFFu];
     }
-    for (uint32_t i = 0; i < 256; ++i)
-      for (int t = 1; t < 8; ++t) tab[t][i] = (tab[t - 1][i] >> 8) ^ tab[0][tab[t - 1][i] & 0xFFu];
-    ready = true;
-  }
+  };
+  static const Table table;  // function-local static: initialised once, thread-safely (C++11)
+  const uint32_t (*tab)[256] = table.t;
   const unsigned char* p = static_cast<const unsigned char*>(data);
   uint32_t c = ~crc;
   while (n >= 8) {

@@ -73,6 +73,7 @@ struct TcCommon {
   int H, W, tiles_x, tiles_y;
   int nphases;
   int phase1_reads_phase0;  // phase 1 TMA-loads tensors that phase 0 of the same CTA wrote (conv1 -> conv10)
+  float trunc_comp;         // see conv_tc_dev.cuh
   long long* trace;  // debug (PFNL_TC_TRACE=1): clock64 stamps of CTA 0, [role][event]; else NULL
 };
 
@@ -170,6 +171,7 @@ __device__ __forceinline__ void epilogue_phase(const TcPhase& P, const TcCommon&
   E.out_f32 = P.out_f32;
   E.H = cm.H;
   E.W = cm.W;
+  E.trunc_comp = cm.trunc_comp;
   U256 pre[2];  // 16 fp32: partial sums (kept across the unit's frames) or previous fp32 content
 #pragma unroll
   for (int j = 0; j < 8; ++j) pre[0].w[j] = pre[1].w[j] = 0u;
@@ -502,8 +504,9 @@ template <int NSPLIT>
 __global__ void __launch_bounds__(128) conv0_tc_kernel(const float* __restrict__ inp21, int H, int W, int tiles_x,
                                                        int tiles_y, int ntiles, const __half* __restrict__ wimg,
                                                        const float* __restrict__ bias, __half* __restrict__ out_hi,
-                                                       __half* __restrict__ out_lo) {
+                                                       __half* __restrict__ out_lo, float trunc_comp) {
   using CF = Conv0Cfg<NSPLIT>;
+  const float comp = 1.f + trunc_comp * 6.f * 1.1920929e-7f;  // chain of 5 accumulating MMAs (conv_tc_dev.cuh)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_sm = smem;                                  // [NSPLIT][KC][128 rows][16 B]
@@ -624,7 +627,7 @@ __global__ void __launch_bounds__(128) conv0_tc_kernel(const float* __restrict__
       __half* pl = reinterpret_cast<__half*>(&ol);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float v = __uint_as_float(d0[j]);
+        float v = __uint_as_float(d0[j]) * comp;
         if (NSPLIT == 2) v = fmaf(__uint_as_float(d1[j]), 1.f / 2048.f, v);
         v = lrelu(v + bias_sm[c0 + j]);
         if (NSPLIT == 2)
@@ -669,8 +672,9 @@ int phase_sources(TcPhase& ph, const void* src_hi, const void* src_lo, int src_i
 
 // Launches one persistent kernel running phase a and (optionally) phase b on the same units.
 template <class P0, class P1, int NSPLIT>
-int launch_tc(const TcProgram& prog, int nphases, bool phase1_reads_phase0, int H, int W, int num_sms,
+int launch_tc(const TcProgram& prog, int nphases, bool phase1_reads_phase0, int H, int W, const TcWeights& tw,
               cudaStream_t s) {
+  const int num_sms = tw.num_sms;
   const TcPhase& a = prog.ph[0];
   using KC = KernelCfg<P0, P1, NSPLIT>;
   TcCommon cm;
@@ -681,6 +685,7 @@ int launch_tc(const TcProgram& prog, int nphases, bool phase1_reads_phase0, int 
   cm.tiles_y = ceil_div(H, 16);
   cm.nphases = nphases;
   cm.phase1_reads_phase0 = (nphases > 1 && phase1_reads_phase0) ? 1 : 0;
+  cm.trunc_comp = tw.trunc_comp;
   if (a.n_units <= 0) return PFNL_OK;
   for (int i = 1; i < nphases; ++i)
     if (prog.ph[i].n_units != a.n_units) {
@@ -822,6 +827,7 @@ int tc_init(TcWeights& tw, int precision, const TcRawWeights& raw, std::vector<v
   PFNL_CUDA(cudaGetDeviceProperties(&prop, dev));
   tw.num_sms = prop.multiProcessorCount;
   tw.flow = tc_flow_default();
+  tw.trunc_comp = getenv("PFNL_TC_TRUNC_COMP") != nullptr ? (float)atof(getenv("PFNL_TC_TRUNC_COMP")) : kTcTruncCompDefault;
   tw.precision = precision;
   tw.nsplit = tc_nsplit(precision);
   tw.raw = raw;
@@ -920,7 +926,7 @@ int pfrb_tc(const TcWeights& tw, TcWorkspace& w, int i, int N, int H, int W, cud
   b.out_hi = (__half*)w.base[0];
   b.out_lo = (__half*)w.base[1];
   if (prof) prof->begin(kProfConv1, s);
-  rc = launch_tc<typename SH::C3, typename SH::C10, NSPLIT>(prog, 2, true, H, W, tw.num_sms, s);
+  rc = launch_tc<typename SH::C3, typename SH::C10, NSPLIT>(prog, 2, true, H, W, tw, s);
   if (prof) prof->end(s);
   if (rc) return rc;
   // ---- launch B: conv2_i(concat[base, inp1[t]]) = conv(base; W2[:,:,0:64]) + conv(inp1[t]; W2[:,:,64:128]):
@@ -949,7 +955,7 @@ int pfrb_tc(const TcWeights& tw, TcWorkspace& w, int i, int N, int H, int W, cud
   b.out_hi = (__half*)w.actA[0];
   b.out_lo = (__half*)w.actA[1];
   if (prof) prof->begin(kProfConv2, s);
-  rc = launch_tc<typename SH::C3, typename SH::C3, NSPLIT>(prog, 2, false, H, W, tw.num_sms, s);
+  rc = launch_tc<typename SH::C3, typename SH::C3, NSPLIT>(prog, 2, false, H, W, tw, s);
   if (prof) prof->end(s);
   if (rc) return rc;
   *launches += 2;
@@ -983,7 +989,8 @@ int conv0_tc(const TcWeights& tw, TcWorkspace& w, const float* inp21, int N, int
     cfg.attrs = attr;
     cfg.numAttrs = na;
     PFNL_CUDA(cudaLaunchKernelEx(&cfg, conv0_tc_kernel<NSPLIT>, inp21, H, W, tiles_x, tiles_y, ntiles,
-                                 (const __half*)tw.conv0, tw.raw.conv0_b, (__half*)w.actA[0], (__half*)w.actA[1]));
+                                 (const __half*)tw.conv0, tw.raw.conv0_b, (__half*)w.actA[0], (__half*)w.actA[1],
+                                 tw.trunc_comp));
   }
   PFNL_LAUNCH_CHECK();
   return PFNL_OK;
@@ -1012,7 +1019,7 @@ int merge1_tc(const TcWeights& tw, TcWorkspace& w, int N, int H, int W, float* m
     a.bias = t == kFrames - 1 ? tw.raw.merge1_b : nullptr;
     a.out_f32 = merge;
   }
-  return launch_tc<typename SH::CM, typename SH::CM, NSPLIT>(prog, kFrames, false, H, W, tw.num_sms, s);
+  return launch_tc<typename SH::CM, typename SH::CM, NSPLIT>(prog, kFrames, false, H, W, tw, s);
 }
 
 template <int NSPLIT>

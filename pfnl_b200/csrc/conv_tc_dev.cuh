@@ -162,7 +162,24 @@ struct TcEpiArgs {
   const __half* res_lo;
   float* out_f32;            // [out_images][H][W][NOUT]
   int H, W;
+  float trunc_comp;          // kappa of the truncation-bias compensation below (0: off)
 };
+
+// TMEM accumulation truncates toward zero (probes/umma_probe.cu): every accumulating MMA loses on average half an
+// ulp of the running sum, in the direction of zero - a bias, not noise.  For a sum built from zero-mean terms
+// (Xavier/zero-mean weights) E[s_k | s_K] = (k/K) s_K, and ulp(s)/|s| averages 0.72 * 2^-23 over a binade, so the
+// expected loss of a chain of K accumulations is 0.36 * 2^-23 * sum_k s_k = kappa * (K+1) * 2^-23 * s_K with
+// kappa = 0.18.  The epilogue multiplies each chain's D0 by 1 + kappa (K+1) 2^-23: what remains of the
+// truncation is its zero-mean part, as with round-to-nearest.  (D1 carries the 2^-11-scaled cross terms; its
+// truncation is three orders of magnitude below.)  Number of accumulating MMAs of chain c in one tile:
+template <class PC>
+__device__ __forceinline__ constexpr int tc_chain_len(int c) {
+  int n = 0;
+  for (int s = 0; s < PC::NSRC; ++s)
+    for (int tp = 0; tp < PC::TAPS; ++tp)
+      if (tc_chain<PC::KS, PC::NCH>(tp, s) == c) n += 4;
+  return n;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // per-tile bodies of the three warp roles
@@ -339,11 +356,14 @@ __device__ __forceinline__ void epi_tile(const TcEpiArgs& P, TcBars* bars, const
       if (NSPLIT == 2) tmem_ld_32x32b_x16(t0 + c * CH_STRIDE + NOUT, d1[c]);
     }
     tmem_ld_wait();
+    float comp[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) comp[c] = 1.f + P.trunc_comp * (float)(tc_chain_len<PC>(c) + 1) * 1.1920929e-7f;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      float a = __uint_as_float(d0[0][j]);
+      float a = __uint_as_float(d0[0][j]) * comp[0];
 #pragma unroll
-      for (int c = 1; c < NCH; ++c) a += __uint_as_float(d0[c][j]);
+      for (int c = 1; c < NCH; ++c) a = fmaf(__uint_as_float(d0[c][j]), comp[c], a);
       if (NSPLIT == 2) {
         float b = __uint_as_float(d1[0][j]);
 #pragma unroll

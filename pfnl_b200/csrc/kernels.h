@@ -21,7 +21,8 @@ enum ProfKind {
   kProfTail = 7,
   kProfOther = 8,
   kProfPfrbFlow = 9,  // the whole PFRB stack as one persistent dataflow kernel (pfrb_flow.cu)
-  kProfKinds = 10
+  kProfNlKernel = 10,  // nl_tc_kernel alone (stage entry pfnl_nonlocal only; inside kProfNonlocal in the forward)
+  kProfKinds = 11
 };
 struct Profiler {
   bool on = false;

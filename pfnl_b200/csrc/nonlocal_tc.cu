@@ -10,7 +10,8 @@
 //                    exchanged through smem, exp / sum thread-local), P (fp16) -> smem, O += P V
 //                    (tcgen05), LAZY running-max correction of the TMEM-resident O (tcgen05.ld/st
 //                    only when the row max grows by more than 8: P <= e^8 stays far inside fp16 and
-//                    the common scale cancels in Y = O / l).
+//                    the common scale cancels in Y = O / l).  l itself is an output column: V carries an all-ones
+//                    channel, so sum_j P_ij is accumulated in TMEM exactly like the values (same truncation).
 //                    The L x L matrix (utils.py:53-58) is never materialised.
 //   then             Z = Y*(Wg*Ww)+(bg*Ww+bw), depth_to_space, + input  (nl_linear_scatter, nonlocal_ffma.cu)
 //
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(kNlThreads, 1)
     const int half = (warp - 2) >> 2;     // 0: keys 0..63 / O columns 0..47 ; 1: keys 64..127 / O columns 48..95
     const int row = qd * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;  // m_run: the reference max the exponentials are taken against
+    float m_run = -INFINITY;  // the reference max the exponentials are taken against
     for (int j = 0; j < ntiles; ++j) {
       const int sb = j % CF::SBUFS, sph = (j / CF::SBUFS) & 1;
       const int pb = j % CF::PBUFS;
@@ -329,7 +330,6 @@ __global__ void __launch_bounds__(kNlThreads, 1)
       const float m_new = bump ? mt : m_run;
       const float alpha = bump ? __expf(m_run - m_new) : 1.f;  // first tile: exp(-inf) = 0, O and l are empty
       m_run = m_new;
-      float psum = 0.f;
       // O may only be rescaled once every PV product issued so far has landed (they complete in order)
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
         mbar_wait(&ctl->pv_done[(j - 1) % CF::PBUFS], ((j - 1) / CF::PBUFS) & 1);
@@ -354,14 +354,12 @@ __global__ void __launch_bounds__(kNlThreads, 1)
           for (int i = 0; i < 8; ++i) {
             const float pv = __expf(__uint_as_float(sreg[c][g8 * 8 + i]) - m_new);
             hp[i] = __float2half_rn(pv);
-            psum += __half2float(hp[i]);
           }
           const int chunk = half * 8 + c * 4 + g8;  // 16-byte chunk index along the 128 keys
           const uint32_t off = (chunk >> 3) * (kQT * 128) + sw128_offset(row, chunk & 7);
           *reinterpret_cast<uint4*>(pbuf + off) = *reinterpret_cast<const uint4*>(hp);
         }
       }
-      l_run = l_run * alpha + psum;
       fence_proxy_async();   // make the generic-proxy P writes visible to the tensor-core (async) proxy
       fence_before_sync();
       __syncwarp();
@@ -369,17 +367,7 @@ __global__ void __launch_bounds__(kNlThreads, 1)
     }
     mbar_wait(&ctl->pv_done[(ntiles - 1) % CF::PBUFS], ((ntiles - 1) / CF::PBUFS) & 1);
     fence_after_sync();
-    // l of the row = sum of the two half-row sums (both were kept against the same reference max)
-    ctl->rowsum[half][row] = l_run;
-    asm volatile("bar.sync 1, %0;" ::"n"(kNlSoftmaxWarps * 32) : "memory");
-    const float l_tot = l_run + ctl->rowsum[half ^ 1][row];
-    const float inv = ksplit > 1 ? 1.f : 1.f / l_tot;  // partials stay un-normalised
     const int q = q0 + row;
-    if (ksplit > 1 && half == 0 && q < L) {
-      float* ml = ML + (((long long)split * gridDim.y + n) * L + q) * 2;
-      ml[0] = m_run;
-      ml[1] = l_tot;
-    }
     {
       uint32_t o[32];
       uint32_t o2[16];
@@ -399,6 +387,20 @@ __global__ void __launch_bounds__(kNlThreads, 1)
           o2[i] = __float_as_uint(fmaf(__uint_as_float(ol2[i]), 1.f / 2048.f, __uint_as_float(o2[i])));
       }
       tmem_ld_wait();
+      // The softmax denominator is taken from the accumulator itself: V's first padding channel (84) is all ones,
+      // so O[:,84] = sum_j P_ij went through exactly the same sequence of truncating TMEM accumulations (and lazy
+      // rescalings) as the value columns - the toward-zero bias of long accumulation chains (8 per key tile: 256
+      // at L = 4096) is common to numerator and denominator and cancels in Y = O / O[:,84], whatever the shape of
+      // the attention row.  Column 84 lives in the half-1 thread: o2[84 - 48 - 32].
+      if (half == 1) ctl->rowsum[1][row] = __uint_as_float(o2[kNL - 48 - 32]);
+      asm volatile("bar.sync 1, %0;" ::"n"(kNlSoftmaxWarps * 32) : "memory");
+      const float l_tot = ctl->rowsum[1][row];
+      const float inv = ksplit > 1 ? 1.f : 1.f / l_tot;  // partials stay un-normalised
+      if (ksplit > 1 && half == 0 && q < L) {
+        float* ml = ML + (((long long)split * gridDim.y + n) * L + q) * 2;
+        ml[0] = m_run;
+        ml[1] = l_tot;
+      }
       if (q < L) {
         float* dst = (ksplit > 1 ? Ypart + (long long)split * gridDim.y * L * kNL : Y) +
                      ((long long)n * L + q) * kNL + half * 48;
@@ -510,7 +512,9 @@ __global__ void __launch_bounds__(256) nl_prep_kernel(const float* __restrict__ 
   }
   for (int i = tid; i < kVR * 64; i += 256) {   // Xt16 rows (token-contiguous)
     const int c = i >> 6, tl = i & 63;
-    const float v = c < kNL ? xs[tl * (kNL + 1) + c] : 0.f;
+    // row 84 (the first padding channel) is all ones: its output column accumulates sum_j P_ij in TMEM next to
+    // the value columns, see the normalisation in nl_tc_kernel
+    const float v = c < kNL ? xs[tl * (kNL + 1) + c] : (c == kNL ? 1.f : 0.f);
     const __half hi = __float2half_rn(v);
     const long long o = ((long long)n * kVR + c) * Lp + t0 + tl;
     Xt16[o] = hi;
@@ -537,7 +541,8 @@ int tc_nl_init() {
 
 // `lr` != NULL: gather the tokens from the LR clip [N,7,H,W,3] (L = H/2 * W/2), `tokens` unused
 static int run_nl_tc(const float* tokens, const float* lr, int H, int W, int N, int L, int nsplit, __half* x16,
-                     __half* gt16, float* Y, float* part, int sms, cudaStream_t s, int* launches_out) {
+                     __half* gt16, float* Y, float* part, int sms, cudaStream_t s, int* launches_out,
+                     Profiler* kprof = nullptr) {
   const int Lp = ceil_div(L, kKT) * kKT;
   const long long x_plane = (long long)N * Lp * kCP, g_plane = (long long)N * kVR * Lp;
   dim3 pg(Lp / 64, N);
@@ -556,10 +561,12 @@ static int run_nl_tc(const float* tokens, const float* lr, int H, int W, int N, 
   float* ypart = part;
   float* ml = part != nullptr ? part + (size_t)ksplit * N * L * kNL : nullptr;
   dim3 grid(Lp / kQT, N, ksplit);
+  if (kprof) kprof->begin(kProfNlKernel, s);
   if (nsplit == 2)
     nl_tc_kernel<2><<<grid, kNlThreads, NlCfg<2>::SMEM, s>>>(tmx, tmxl, tmg, tmgl, L, Lp, Y, ksplit, ypart, ml);
   else
     nl_tc_kernel<1><<<grid, kNlThreads, NlCfg<1>::SMEM, s>>>(tmx, tmxl, tmg, tmgl, L, Lp, Y, ksplit, ypart, ml);
+  if (kprof) kprof->end(s);
   PFNL_LAUNCH_CHECK();
   *launches_out = 2;
   if (ksplit > 1) {
@@ -604,7 +611,7 @@ int tc_nonlocal(const TcWeights& tw, TcWorkspace& w, const float* tokens, const 
 }
 
 int tc_nonlocal_tokens(const TcWeights& tw, const float* tokens, int N, int L, float* out, cudaStream_t s,
-                       long long* launches) {
+                       long long* launches, Profiler* prof) {
   // stage-level entry (pfnl_nonlocal): grow-only scratch owned by the process (isolation benchmarks)
   static uint8_t* scratch = nullptr;
   static size_t cap = 0;
@@ -628,7 +635,8 @@ int tc_nonlocal_tokens(const TcWeights& tw, const float* tokens, int N, int L, f
   float* y = (float*)(scratch + b_x + b_g);
   float* part = b_p ? (float*)(scratch + b_x + b_g + b_y) : nullptr;
   int nl = 0;
-  int rc = run_nl_tc(tokens, nullptr, 0, 0, N, L, tc_nl_nsplit(tw.precision), x16, gt16, y, part, tw.num_sms, s, &nl);
+  int rc = run_nl_tc(tokens, nullptr, 0, 0, N, L, tc_nl_nsplit(tw.precision), x16, gt16, y, part, tw.num_sms, s, &nl,
+                     prof);
   if (rc == PFNL_OK) rc = launch_nl_linear(y, N * L, tw.raw.nl_gw_w, tw.raw.nl_gw_b, out, s);
   if (rc) return rc;
   *launches += nl + 1;

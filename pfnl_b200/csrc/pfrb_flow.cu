@@ -67,6 +67,7 @@ struct alignas(64) FlowParams {
   int H, W, tiles_x, tiles_y, n_units;
   int blk0, nblk, buf0;
   int n_role[4];
+  float trunc_comp;
 };
 
 template <int NSPLIT>
@@ -367,6 +368,7 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
         E.out_f32 = p.pbase;
         E.H = p.H;
         E.W = p.W;
+        E.trunc_comp = p.trunc_comp;
         for (int item = rank; item < n_items; item += nr, ++it) {
           const FlowItem f = flow_item(p, role, item);
           if (warp == 2) mark(4, 1, b, item);
@@ -531,6 +533,7 @@ int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int buf
   p.blk0 = blk0;
   p.nblk = nblk;
   p.buf0 = buf0;
+  p.trunc_comp = tw.trunc_comp;
   // role split of the grid ~ MMA work per block (conv1 252 : conv10 28 : conv2b 36 : conv2f 252 k-steps per
   // unit), conv10 rounded up because its tiles are fill-bound: 64 / 10 / 10 / 64 of 148
   const int G = tw.num_sms;

@@ -16,6 +16,7 @@ namespace pfnl {
 // the UMMA descriptor base-offset convention.  Settled by probes/umma_probe.cu on a B200 (see
 // DESIGN.md): the swizzle is a function of the absolute smem address, so a pitch of 10 pixels
 // (no padding) with base_offset = 0 is exact; base_offset = (start>>7)&7 is WRONG on B200.
+constexpr float kTcTruncCompDefault = 0.18f;  // = the model's value; calibration: profiles/r2f_trunc_comp.txt
 constexpr int kTcPatchW3 = 10;
 constexpr int kTcBaseOffsetMode = 0;
 
@@ -62,6 +63,7 @@ struct TcWeights {
   void* conv0 = nullptr;  // [10 k-chunks][nsplit*64 rows][8 k] fp16, un-swizzled core matrices (conv0_tc_kernel)
   float* zero_bias = nullptr;  // [64] zeros
   bool flow = true;            // PFRB stack as the persistent dataflow kernel (pfnl_set_flow / PFNL_TC_FLOW=0: phase kernels)
+  float trunc_comp = 0.f;      // kappa of the TMEM truncation-bias compensation (conv_tc_dev.cuh); PFNL_TC_TRUNC_COMP
   int num_sms = 0;             // SM count of the handle's device (grid size of the persistent kernels)
   // non-local (precision 2): fp16 Wg^T image etc.
   void* nl_priv = nullptr;
@@ -98,7 +100,7 @@ int tc_nonlocal(const TcWeights& tw, TcWorkspace& w, const float* tokens, const 
                 float* inp21, cudaStream_t s, long long* launches, Profiler* prof);
 // tokens [N,L,84] -> NonLocalBlock output [N,L,84]
 int tc_nonlocal_tokens(const TcWeights& tw, const float* tokens, int N, int L, float* out, cudaStream_t s,
-                       long long* launches);
+                       long long* launches, Profiler* prof);
 // The PFRB stack as one persistent dataflow kernel (pfrb_flow.cu): blocks [blk0, blk0+nblk) on the fp16 planes;
 // input in inp0 buffer `buf0` (0 = actA, 1 = actA2), output in buffer (buf0 + nblk) & 1.
 int* tc_fault_buffer();  // api.cu: host-mapped wait-timeout record (device pointer; may be NULL)

@@ -104,7 +104,7 @@ class Engine:
         return int(lib.pfnl_launch_count(self._h))
 
     PROF_KINDS = ("pack_tokens", "nonlocal", "conv0", "conv1_3x3", "conv10_1x1", "conv2_3x3", "convmerge1",
-                  "tail", "other", "pfrb_flow")
+                  "tail", "other", "pfrb_flow", "nl_tc_kernel")
 
     def set_flow(self, enable):
         """Tensor-core precisions: PFRB stack as one persistent dataflow kernel (default) or two launches per block."""
@@ -141,8 +141,25 @@ class Engine:
         return out
 
     def forward_host(self, x, out=None):
-        """numpy / CPU-tensor in, numpy out (H2D + forward + D2H inside the call)."""
-        xt = torch.as_tensor(x, dtype=torch.float32).contiguous()
+        """numpy / CPU-tensor in, CPU tensor out (H2D + forward + D2H inside the call)."""
+        ticket, out = self.forward_host_submit(x, out)
+        self.forward_host_wait(ticket)
+        return out
+
+    def forward_host_submit(self, x, out=None):
+        """Pipelined form of forward_host: starts H2D -> forward -> D2H for one batch and returns (ticket, out);
+        `out` is complete after forward_host_wait(ticket).  Submitting the next batch before waiting overlaps the
+        copies with compute (two staging slots: at most two batches in flight).  float64 input (what the
+        reference feeds, pfnl.py:209,252) is narrowed inside the library on its way into pinned staging; the
+        caller must keep `x` unchanged only until this call returns, `out` alive until the wait."""
+        xt = torch.as_tensor(x)
+        if xt.is_cuda:
+            raise ValueError("forward_host takes host memory; use forward() for CUDA tensors")
+        if xt.dtype not in (torch.float32, torch.float64):
+            xt = xt.to(torch.float32)
+        xt = xt.contiguous()
+        if xt.dim() != 5:
+            raise ValueError(f"input must be [N,7,H,W,3], got {tuple(xt.shape)}")
         n, f, h, w, c = xt.shape
         if f != _lib.NUM_FRAMES or c != 3:
             raise ValueError(f"input must be [N,7,H,W,3], got {tuple(xt.shape)}")
@@ -151,10 +168,20 @@ class Engine:
         elif not (isinstance(out, torch.Tensor) and not out.is_cuda and out.dtype == torch.float32
                   and out.is_contiguous() and tuple(out.shape) == (n, 1, h * 4, w * 4, 3)):
             raise ValueError(f"out must be a contiguous float32 CPU tensor of shape {(n, 1, h * 4, w * 4, 3)}")
+        ticket = C.c_int(-1)
         with torch.cuda.device(self.device):
-            check(lib.pfnl_forward_host(self._h, C.c_void_p(xt.data_ptr()), n, h, w, C.c_void_p(out.data_ptr()),
-                                        _stream_ptr(self.device)))
-        return out
+            check(lib.pfnl_forward_host_submit(self._h, C.c_void_p(xt.data_ptr()), 1 if xt.dtype == torch.float64 else 0,
+                                               n, h, w, C.c_void_p(out.data_ptr()), _stream_ptr(self.device),
+                                               C.byref(ticket)))
+        return ticket.value, out
+
+    def forward_host_wait(self, ticket):
+        with torch.cuda.device(self.device):
+            check(lib.pfnl_forward_host_wait(self._h, ticket))
+
+    def graph_stats(self):
+        """(executables instantiated, executables re-pointed in place, executables cached)."""
+        return tuple(int(lib.pfnl_graph_stats(self._h, k)) for k in range(3))
 
     def mse(self, sr, hr):
         self._chk_in(sr, 5)

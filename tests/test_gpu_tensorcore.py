@@ -292,3 +292,74 @@ def test_convmerge1_stage(tc_engines, prec, tol, regime, shape):
     assert out.shape == (n, h, w, 48)
     assert err.max() <= tol * scale
     assert err[:, [0, -1]].max() <= tol * scale and err[:, :, [0, -1]].max() <= tol * scale
+
+
+# ---- the 1e-3 gate of the headline precision, with margin (VERDICT r1 "what's weak" 1-2) -------------------------
+GATE = 1e-3
+MARGIN_TOL = 0.7 * GATE   # every check below must leave >= 30 % of the gate unused
+
+
+def _oracle_clip_fp64(args):
+    regime, clip = args
+    import numpy as _np
+    from oracle import pfnl_ref as _R
+    return _R.pfnl_forward(clip[None], _R.make_weights(regime), dtype=_np.float64, backend="numpy")[0]
+
+
+def oracle_fp64_parallel(x, regime):
+    """fp64 numpy oracle, one process per clip (single-threaded BLAS each): 128 clips in tens of seconds."""
+    import multiprocessing as mp
+    keys = ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")
+    old = {k: os.environ.get(k) for k in keys}
+    os.environ.update({k: "1" for k in keys})
+    try:
+        workers = max(1, min(32, len(os.sched_getaffinity(0)), x.shape[0]))
+        with mp.get_context("spawn").Pool(workers) as pool:
+            out = pool.map(_oracle_clip_fp64, [(regime, x[i]) for i in range(x.shape[0])], chunksize=1)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return np.stack(out)
+
+
+@pytest.mark.parametrize("regime", ["A", "B"])
+def test_gate_fp16x3_vs_fp32_and_fp64_oracle(tc_engines, regime):
+    """BASELINE config 1: the reference computes in fp32, so the headline precision is held against the fp32 numpy
+    oracle as well as against the fp64 evaluation, both with 30 % margin."""
+    x = R.make_input(1, 32, 32)
+    W = R.make_weights(regime)
+    y = tc_engines[("fp16x3", regime)].forward(cu(x)).cpu().numpy()
+    ref64 = np.load(os.path.join(GOLD, f"forward_{regime}_1x32x32.npz"))["y64"]
+    ref32 = R.pfnl_forward(x, W, dtype=np.float32, backend="numpy")
+    e64, e32 = np.abs(y - ref64).max(), np.abs(y - ref32).max()
+    print(f"fp16x3 regime {regime}: vs fp64 {e64:.3e}, vs fp32 oracle {e32:.3e} (oracle fp32 vs fp64 {np.abs(ref32 - ref64).max():.3e})")
+    assert e64 <= MARGIN_TOL and e32 <= MARGIN_TOL
+
+
+def test_gate_fp16x3_config3_128_clips(tc_engines):
+    """BASELINE config 3's batch: 128 distinct clips (16 per GPU x 8) in regime A - the max over all of them, not
+    one seed.  Run as 8 batches of 16 (the per-GPU shape); also bit-equal to one batch of 128."""
+    x = R.make_input(128, 32, 32, seed=4242)
+    eng = tc_engines[("fp16x3", "A")]
+    ys = torch.cat([eng.forward(cu(x[i:i + 16])) for i in range(0, 128, 16)])
+    y_all = eng.forward(cu(x))
+    torch.cuda.synchronize()
+    assert torch.equal(ys, y_all)
+    ref = oracle_fp64_parallel(x, "A")
+    err = np.abs(ys.cpu().numpy() - ref).reshape(128, -1).max(1)
+    print(f"fp16x3 regime A, 128 clips: max-abs per clip min {err.min():.3e} median {np.median(err):.3e} max {err.max():.3e}")
+    assert err.max() <= MARGIN_TOL
+
+
+def test_gate_fp16x3_config4_128x128_regime_A(tc_engines):
+    """BASELINE config 4 (1 clip x 7 x 128x128, L = 4096 tokens) in regime A against the fp64 oracle: long
+    accumulation chains in the non-local block (256 per row), key-split partials, 128 spatial tiles."""
+    x = R.make_input(1, 128, 128, seed=77)
+    y = tc_engines[("fp16x3", "A")].forward(cu(x)).cpu().numpy()
+    ref = R.pfnl_forward(x, R.make_weights("A"), dtype=np.float64, backend="numpy")
+    err = np.abs(y - ref).max()
+    print(f"fp16x3 regime A 1x128x128: |out|max {np.abs(ref).max():.1f} max-abs vs fp64 {err:.3e}")
+    assert err <= MARGIN_TOL
