@@ -826,6 +826,7 @@ int tc_init(TcWeights& tw, int precision, const TcRawWeights& raw, std::vector<v
   PFNL_CUDA(cudaGetDevice(&dev));
   PFNL_CUDA(cudaGetDeviceProperties(&prop, dev));
   tw.num_sms = prop.multiProcessorCount;
+  PFNL_CUDA(tc_apply_wait_limit_from_env());
   tw.flow = tc_flow_default();
   tw.trunc_comp = getenv("PFNL_TC_TRUNC_COMP") != nullptr ? (float)atof(getenv("PFNL_TC_TRUNC_COMP")) : kTcTruncCompDefault;
   tw.precision = precision;

@@ -534,6 +534,7 @@ bool tc_has_nonlocal() { return true; }
 int tc_nl_nsplit(int precision) { return precision == PFNL_PREC_TC_FP16X3 ? 2 : 1; }
 
 int tc_nl_init() {
+  PFNL_CUDA(tc_apply_wait_limit_from_env());
   PFNL_CUDA(cudaFuncSetAttribute(nl_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, NlCfg<1>::SMEM));
   PFNL_CUDA(cudaFuncSetAttribute(nl_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, NlCfg<2>::SMEM));
   return PFNL_OK;

@@ -115,6 +115,21 @@ __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// The count of items whose inputs have been acquired travels from the dependency warp to the TMA thread and the
+// conv2 epilogue warps through one shared-memory word, release/acquire at CTA scope.  Both sides use atomics so
+// that the word is only ever touched atomically (compute-sanitizer racecheck models barriers and atomics, not
+// release/acquire on plain accesses: profiles/r2i_sanitizer.txt).
+__device__ __forceinline__ void deps_seen_store(int* p, int v) {
+  int old;
+  asm volatile("atom.release.cta.shared::cta.exch.b32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+  (void)old;
+}
+__device__ __forceinline__ int deps_seen_load(int* p) {
+  int v;
+  asm volatile("atom.acquire.cta.shared::cta.or.b32 %0, [%1], 0;" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+
 struct FlowItem {
   int u, t, tx, ty, nimg;
 };
@@ -265,11 +280,7 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
       if (lane == 0) {
         TcRing rg{0, 0};
         int nissued = 0;
-        auto seen = [&]() {
-          int v;
-          asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&ctl->deps_seen)) : "memory");
-          return v;
-        };
+        auto seen = [&]() { return deps_seen_load(&ctl->deps_seen); };
         for (int b = 0; b < p.nblk; ++b) {
           const int pp = (p.buf0 + b) & 1;  // inp0 buffer this block reads
           const CUtensorMap* tm_hi = role == kRoleConv1    ? &p.tmA[pp][0]
@@ -376,19 +387,18 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
             // the partial sums of this unit come from a conv2b CTA and are read with generic loads: wait until the
             // producer warp has acquired this item's counters (CTA-scope acquire of its count; the loads
             // themselves go past the L1, conv_tc_dev.cuh)
-            auto seen = [&]() {
-              int v;
-              asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&ctl->deps_seen)) : "memory");
-              return v;
+            auto seen = [&]() {  // one atomic per warp, broadcast
+              int v = 0;
+              if (lane == 0) v = deps_seen_load(&ctl->deps_seen);
+              return __shfl_sync(0xffffffffu, v, 0);
             };
-            if (__any_sync(0xffffffffu, seen() <= it)) {
+            if (seen() <= it) {
               const long long t0 = clock64();
               while (seen() <= it) {
                 __nanosleep(64);
                 if (clock64() - t0 > kTcWaitLimitCycles) wait_timeout_trap(p.fault, 5, b, item);
               }
             }
-            __syncwarp();
           }
           epi_tile<PC, NSPLIT, FC::TMEM_BUF_COLS, FC::CH_STRIDE>(E, bars, ctl->bias[b], tmem, it, warp, lane,
                                                                  per_frame ? f.nimg * kFrames + f.t : f.nimg, f.nimg,
@@ -415,8 +425,7 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
           flow_deps_ready(p, role, b, f, lane, true, dummy);
           ++nseen;
           if (lane == 0)
-            asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(&ctl->deps_seen)), "r"(nseen)
-                         : "memory");
+            deps_seen_store(&ctl->deps_seen, nseen);
           __syncwarp();
         }
     } else if (lane == 0) {
@@ -632,6 +641,7 @@ int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int buf
 }  // namespace
 
 int tc_flow_init() {
+  PFNL_CUDA(tc_apply_wait_limit_from_env());
   PFNL_CUDA(cudaFuncSetAttribute(pfrb_flow_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  FlowCfg<1>::SMEM_BYTES));
   PFNL_CUDA(cudaFuncSetAttribute(pfrb_flow_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,

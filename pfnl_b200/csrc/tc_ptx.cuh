@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace pfnl {
 namespace tc {
@@ -39,7 +40,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // far above anything a correct run reaches (a whole forward is ~2e6 cycles; compute-sanitizer runs are ~100x
 // slower, hence the generous value).  `fault` (optional, host-mapped memory so that it survives the trap)
 // receives {1 + kind, blockIdx.x, a, b} of the first wait that gave up.
-constexpr long long kTcWaitLimitCycles = 6000000000ll;
+constexpr long long kTcWaitLimitDefault = 20000000000ll;
+static __device__ long long g_tc_wait_limit = kTcWaitLimitDefault;  // one copy per translation unit
+#define kTcWaitLimitCycles g_tc_wait_limit
+// Host side, once per translation unit that waits (PFNL_TC_WAIT_LIMIT_CYCLES in the environment: compute-sanitizer
+// runs, where a correct kernel can be orders of magnitude slower).
+static inline cudaError_t tc_apply_wait_limit_from_env() {
+  const char* e = getenv("PFNL_TC_WAIT_LIMIT_CYCLES");
+  if (e == nullptr) return cudaSuccess;
+  const long long v = atoll(e);
+  if (v <= 0) return cudaSuccess;
+  return cudaMemcpyToSymbol(g_tc_wait_limit, &v, sizeof(v));
+}
 static __device__ __noinline__ void wait_timeout_trap(int* fault, int kind, int a, int b) {
   if (fault != nullptr && atomicCAS(fault, 0, 1 + kind) == 0) {
     fault[1] = (int)blockIdx.x;
