@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpfnl_b200.so")
+# PFNL_B200_LIB: another build of the same library (A/B measurements of kernel variants, tools/ab_build.sh)
+LIB_PATH = os.environ.get("PFNL_B200_LIB") or os.path.join(HERE, "libpfnl_b200.so")
 
 NUM_FRAMES = 7
 SCALE = 4

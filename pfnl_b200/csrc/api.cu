@@ -618,7 +618,7 @@ int pfnl_profile(pfnl_handle* h, int enable) {
     return PFNL_ERR_BAD_ARG;
   }
   h->prof.on = enable != 0;
-  tc_set_pdl(!h->prof.on);
+  h->tcw.pdl = !h->prof.on;
   return PFNL_OK;
 }
 

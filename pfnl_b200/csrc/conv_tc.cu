@@ -151,7 +151,7 @@ __device__ __forceinline__ void mma_phase(const TcPhase& P, const TcCommon& cm, 
   for (int u = blockIdx.x; u < P.n_units; u += gridDim.x)
     for (int t = 0; t < P.frames; ++t, ++it)
       mma_tile<PC, NSPLIT, KC::NS, KC::SLOT_BYTES, KC::TMEM_BUF_COLS, KC::CH_STRIDE>(wsm, ring, &ctl->bars, tmem, rg, it,
-                                                                                  lane, tr);
+                                                                                  lane, tr, it);
 }
 
 template <class PC, class KC, int NSPLIT>
@@ -172,6 +172,7 @@ __device__ __forceinline__ void epilogue_phase(const TcPhase& P, const TcCommon&
   E.H = cm.H;
   E.W = cm.W;
   E.trunc_comp = cm.trunc_comp;
+  E.st_policy = 0;
   U256 pre[2];  // 16 fp32: partial sums (kept across the unit's frames) or previous fp32 content
 #pragma unroll
   for (int j = 0; j < 8; ++j) pre[0].w[j] = pre[1].w[j] = 0u;
@@ -183,7 +184,7 @@ __device__ __forceinline__ void epilogue_phase(const TcPhase& P, const TcCommon&
       const int ty = r % cm.tiles_y;
       const int nimg = r / cm.tiles_y;
       epi_tile<PC, NSPLIT, KC::TMEM_BUF_COLS, KC::CH_STRIDE>(E, &ctl->bars, bias_sm, tmem, it, warp, lane,
-                                                             nimg * P.frames + t, nimg, tx, ty, t == 0, pre, tr, nohook);
+                                                             nimg * P.frames + t, nimg, tx, ty, t == 0, pre, tr, nohook, it);
     }
 }
 
@@ -651,11 +652,11 @@ __global__ void __launch_bounds__(128) conv0_tc_kernel(const float* __restrict__
 // ---- host side --------------------------------------------------------------------------------------------
 namespace {
 
-bool g_pdl = true;
-
-bool pdl_enabled() {
+// programmatic dependent launch: per handle (pfnl_profile turns it off so that per-kernel event intervals do not
+// overlap), PFNL_TC_NO_PDL=1 turns it off for the process
+bool pdl_enabled(const TcWeights& tw) {
   static const bool env_off = getenv("PFNL_TC_NO_PDL") != nullptr;
-  return g_pdl && !env_off;
+  return tw.pdl && !env_off;
 }
 
 // Fills the source-side fields of a phase (tensor maps over fp16 planes [src_images,H,W,64]).
@@ -701,7 +702,7 @@ int launch_tc(const TcProgram& prog, int nphases, bool phase1_reads_phase0, int 
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   int na = 0;
-  if (pdl_enabled()) {
+  if (pdl_enabled(tw)) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
@@ -796,11 +797,10 @@ int pack_weights(const float* hwio, int taps, int cin_total, int ci_off, int cou
 void tc_carve(TcWorkspace& w, int precision, int N, int H, int W, const std::function<char*(size_t)>& take) {
   const int nsplit = tc_nsplit(precision);
   for (int pl = 0; pl < 2; ++pl) {
-    w.actA[pl] = w.actA2[pl] = w.actB[pl] = w.base[pl] = nullptr;
+    w.actA[pl] = w.actB[pl] = w.base[pl] = nullptr;
   }
   for (int pl = 0; pl < nsplit; ++pl) {
     w.actA[pl] = take(plane_bytes(N * kFrames, H, W));
-    w.actA2[pl] = take(plane_bytes(N * kFrames, H, W));
     w.actB[pl] = take(plane_bytes(N * kFrames, H, W));
     w.base[pl] = take(plane_bytes(N, H, W));
   }
@@ -887,9 +887,12 @@ int tc_init(TcWeights& tw, int precision, const TcRawWeights& raw, std::vector<v
   return PFNL_OK;
 }
 
-void tc_destroy(TcWeights&) {}
+void tc_destroy(TcWeights& tw) {
+  if (tw.nl_scratch) cudaFree(tw.nl_scratch);
+  tw.nl_scratch = nullptr;
+  tw.nl_scratch_cap = 0;
+}
 
-void tc_set_pdl(bool on) { g_pdl = on; }
 
 namespace {
 
@@ -982,7 +985,7 @@ int conv0_tc(const TcWeights& tw, TcWorkspace& w, const float* inp21, int N, int
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     int na = 0;
-    if (pdl_enabled()) {
+    if (pdl_enabled(tw)) {
       attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[na].val.programmaticStreamSerializationAllowed = 1;
       ++na;
@@ -1033,9 +1036,9 @@ int trunk_tc(const TcWeights& tw, TcWorkspace& w, const float* inp21, int N, int
   if (rc) return rc;
   *launches += 1;
   if (tw.flow) {
-    // the 20 blocks as one persistent dataflow kernel; 20 is even, so the result is back in actA
+    // the 20 blocks as one persistent dataflow kernel, in place on actA
     if (prof) prof->begin(kProfPfrbFlow, s);
-    rc = tc_pfrb_flow(tw, w, 0, PFNL_NUM_BLOCK, 0, N, H, W, pdl_enabled(), s);
+    rc = tc_pfrb_flow(tw, w, 0, PFNL_NUM_BLOCK, N, H, W, pdl_enabled(tw), s);
     if (prof) prof->end(s);
     if (rc) return rc;
     *launches += 1;
@@ -1068,17 +1071,16 @@ int tc_pfrb_fp32io(const TcWeights& tw, TcWorkspace& w, int precision, int blk, 
   PFNL_LAUNCH_CHECK();
   int rc;
   const bool flow = tw.flow;
-  if (flow) {  // one block through the dataflow kernel: actA -> actA2
-    rc = tc_pfrb_flow(tw, w, blk, 1, 0, N, H, W, false, s);
+  if (flow) {  // one block through the dataflow kernel
+    rc = tc_pfrb_flow(tw, w, blk, 1, N, H, W, false, s);
     *launches += 1;
   } else {
     rc = ns == 2 ? pfrb_tc<2>(tw, w, blk, N, H, W, s, launches, nullptr)
                  : pfrb_tc<1>(tw, w, blk, N, H, W, s, launches, nullptr);
   }
   if (rc) return rc;
-  planes_to_f32_kernel<<<148 * 8, 256, 0, s>>>((const __half*)(flow ? w.actA2[0] : w.actA[0]),
-                                               (const __half*)(flow ? w.actA2[1] : w.actA[1]), n, (long long)H * W,
-                                               ns, frames_out);
+  planes_to_f32_kernel<<<148 * 8, 256, 0, s>>>((const __half*)w.actA[0], (const __half*)w.actA[1], n,
+                                               (long long)H * W, ns, frames_out);
   PFNL_LAUNCH_CHECK();
   *launches += 2;
   return PFNL_OK;

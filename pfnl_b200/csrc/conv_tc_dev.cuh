@@ -105,6 +105,14 @@ __device__ __forceinline__ void st_plane16(__half* p, long long cs, const U256& 
   *reinterpret_cast<uint4*>(p) = make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]);
   *reinterpret_cast<uint4*>(p + cs) = make_uint4(r.w[4], r.w[5], r.w[6], r.w[7]);
 }
+__device__ __forceinline__ void st_plane16_hint(__half* p, long long cs, const U256& r, unsigned long long policy) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(r.w[0]), "r"(r.w[1]), "r"(r.w[2]),
+               "r"(r.w[3]), "l"(policy)
+               : "memory");
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p + cs), "r"(r.w[4]), "r"(r.w[5]),
+               "r"(r.w[6]), "r"(r.w[7]), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ long long globaltimer_ns() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -163,6 +171,7 @@ struct TcEpiArgs {
   float* out_f32;            // [out_images][H][W][NOUT]
   int H, W;
   float trunc_comp;          // kappa of the truncation-bias compensation below (0: off)
+  unsigned long long st_policy;  // L2 eviction hint of the fp16-plane stores (0: none)
 };
 
 // TMEM accumulation truncates toward zero (probes/umma_probe.cu): every accumulating MMA loses on average half an
@@ -188,13 +197,17 @@ __device__ __forceinline__ constexpr int tc_chain_len(int c) {
 // of stage s = ic0 + s; (x0, y0) = top-left pixel of the halo patch (may be negative: zero fill = 'same' padding).
 template <class PC, int NSPLIT, int NS, int SLOT_BYTES>
 __device__ __forceinline__ void load_tile(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, uint8_t* ring,
-                                          TcBars* bars, TcRing& rg, int x0, int y0, int ic0) {
+                                          TcBars* bars, TcRing& rg, int x0, int y0, int ic0, uint64_t l2_policy = 0) {
   for (int s = 0; s < PC::NSRC; ++s) {
 #pragma unroll
     for (int pl = 0; pl < NSPLIT; ++pl) {  // hi plane first (consumed first), then lo
       mbar_wait(&bars->empty[rg.sl], rg.ph ^ 1);
       mbar_arrive_expect_tx(&bars->full[rg.sl], PC::PATCH_BYTES);
-      tma_load_4d(ring + rg.sl * SLOT_BYTES, pl == 1 ? tm_lo : tm_hi, &bars->full[rg.sl], x0 * 8, y0, 0, ic0 + s);
+      if (l2_policy != 0)
+        tma_load_4d_hint(ring + rg.sl * SLOT_BYTES, pl == 1 ? tm_lo : tm_hi, &bars->full[rg.sl], x0 * 8, y0, 0, ic0 + s,
+                         l2_policy);
+      else
+        tma_load_4d(ring + rg.sl * SLOT_BYTES, pl == 1 ? tm_lo : tm_hi, &bars->full[rg.sl], x0 * 8, y0, 0, ic0 + s);
       if (++rg.sl == NS) {
         rg.sl = 0;
         rg.ph ^= 1;
@@ -204,10 +217,10 @@ __device__ __forceinline__ void load_tile(const CUtensorMap* tm_hi, const CUtens
 }
 
 // MMA issuer (converged warp, one elected lane issues): all MMAs of tile number `it` of this CTA.
-//   tr: clock stamps of the traced CTA (or NULL)
+//   tr: clock stamps of the traced CTA (or NULL), tri: index of this tile in the trace window
 template <class PC, int NSPLIT, int NS, int SLOT_BYTES, int TMEM_BUF_COLS, int CH_STRIDE>
 __device__ __forceinline__ void mma_tile(uint8_t* wsm, uint8_t* ring, TcBars* bars, uint32_t tmem, TcRing& rg, int it,
-                                         int lane, long long* tr) {
+                                         int lane, long long* tr, int tri) {
   constexpr int KS = PC::KS, NSRC = PC::NSRC, NOUT = PC::NOUT, NCH = PC::NCH, TAPS = PC::TAPS;
   constexpr int TAP_BYTES = NSPLIT * PC::WT_BYTES;
   constexpr uint32_t idesc_lo = make_idesc_f16(128, NOUT);           // A_lo x W_hi          -> D1
@@ -227,7 +240,7 @@ __device__ __forceinline__ void mma_tile(uint8_t* wsm, uint8_t* ring, TcBars* ba
     // ---- hi-plane pass: [D0_c | D1_c] (+)= A_hi x [W_hi ; W_lo]
     mbar_wait(&bars->full[rg.sl], rg.ph);
     fence_after_sync();
-    if (tr != nullptr && lane == 0 && s == 0 && 1 + 2 * it < 64) tr[64 + 1 + 2 * it] = clock64();
+    if (tr != nullptr && lane == 0 && s == 0 && 1 + 2 * tri < 64) tr[64 + 1 + 2 * tri] = clock64();
     {
       const uint64_t ad = make_sdesc_interleave(smem_u32(ring + rg.sl * SLOT_BYTES), SUB_A, SBO_A);
       if (elect_one()) {
@@ -279,7 +292,7 @@ __device__ __forceinline__ void mma_tile(uint8_t* wsm, uint8_t* ring, TcBars* ba
         rg.ph ^= 1;
       }
     }
-    if (tr != nullptr && lane == 0 && s == NSRC - 1 && 2 + 2 * it < 64) tr[64 + 2 + 2 * it] = clock64();
+    if (tr != nullptr && lane == 0 && s == NSRC - 1 && 2 + 2 * tri < 64) tr[64 + 2 + 2 * tri] = clock64();
   }
 }
 
@@ -295,13 +308,15 @@ struct TcNoHook {
   __device__ __forceinline__ void idle() {}
   __device__ __forceinline__ void before_stores() {}
 };
-template <class PC, int NSPLIT, int TMEM_BUF_COLS, int CH_STRIDE, class Hook>
+// EPI0 = index of the first of the 16 epilogue warps (a multiple of 2 with EPI0 % 4 == warp-quarter alignment kept by
+// `warp & 3`): 2 in the phase kernels (warps 2-17), 4 in the dataflow kernel (warps 4-19, whole warpgroups).
+template <class PC, int NSPLIT, int TMEM_BUF_COLS, int CH_STRIDE, class Hook, int EPI0 = 2>
 __device__ __forceinline__ void epi_tile(const TcEpiArgs& P, TcBars* bars, const float* bias_sm, uint32_t tmem, int it,
                                          int warp, int lane, int img, int nimg, int tx, int ty, bool load_pbase,
-                                         U256 (&pre)[2], long long* tr, Hook& hook) {
+                                         U256 (&pre)[2], long long* tr, Hook& hook, int tri) {
   constexpr int NOUT = PC::NOUT, NCH = PC::NCH;
   const int q = warp & 3;             // TMEM lane quarter this warp may access (hardware restriction)
-  const int c0 = ((warp - 2) >> 2) * 16;
+  const int c0 = ((warp - EPI0) >> 2) * 16;
   const bool chunk_active = c0 < NOUT;
   const int m = q * 32 + lane;        // row of the tile = TMEM lane
   const int my = m >> 3, mx = m & 7;  // pixel inside the 16x8 tile
@@ -343,34 +358,42 @@ __device__ __forceinline__ void epi_tile(const TcEpiArgs& P, TcBars* bars, const
     mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
   }
   fence_after_sync();
-  if (tr != nullptr && warp == 2 && lane == 0 && 2 * it < 64) tr[128 + 2 * it] = clock64();
+  if (tr != nullptr && warp == EPI0 && lane == 0 && 2 * tri < 64) tr[128 + 2 * tri] = clock64();
   float v[16];
   if (chunk_active) {
     // chain c: D0 at c*CH_STRIDE, D1 (split mode) at c*CH_STRIDE + NOUT.  Chains are summed in
     // fp32 round-to-nearest here; D1 carries the 2^-11-scaled cross terms.
     const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + buf * TMEM_BUF_COLS + c0;
-    uint32_t d0[NCH][16], d1[NSPLIT == 2 ? NCH : 1][16];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      tmem_ld_32x32b_x16(t0 + c * CH_STRIDE, d0[c]);
-      if (NSPLIT == 2) tmem_ld_32x32b_x16(t0 + c * CH_STRIDE + NOUT, d1[c]);
-    }
-    tmem_ld_wait();
+    // (two rounds of loads - D0 chains, then D1 chains - instead of one: 32 fewer live registers at the peak; the
+    //  epilogue warps run at the 96-register cap of a 640-thread CTA and spilled with all four slices in flight)
     float comp[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) comp[c] = 1.f + P.trunc_comp * (float)(tc_chain_len<PC>(c) + 1) * 1.1920929e-7f;
+    {
+      uint32_t d0[NCH][16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float a = __uint_as_float(d0[0][j]) * comp[0];
+      for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x16(t0 + c * CH_STRIDE, d0[c]);
+      tmem_ld_wait();
 #pragma unroll
-      for (int c = 1; c < NCH; ++c) a = fmaf(__uint_as_float(d0[c][j]), comp[c], a);
-      if (NSPLIT == 2) {
+      for (int j = 0; j < 16; ++j) {
+        float a = __uint_as_float(d0[0][j]) * comp[0];
+#pragma unroll
+        for (int c = 1; c < NCH; ++c) a = fmaf(__uint_as_float(d0[c][j]), comp[c], a);
+        v[j] = a;
+      }
+    }
+    if (NSPLIT == 2) {
+      uint32_t d1[NCH][16];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x16(t0 + c * CH_STRIDE + NOUT, d1[c]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
         float b = __uint_as_float(d1[0][j]);
 #pragma unroll
         for (int c = 1; c < NCH; ++c) b += __uint_as_float(d1[c][j]);
-        a = fmaf(b, 1.f / 2048.f, a);
+        v[j] = fmaf(b, 1.f / 2048.f, v[j]);
       }
-      v[j] = a;
     }
   }
   // this warp's tcgen05.ld are complete: hand the TMEM buffer back before the global stores
@@ -425,15 +448,20 @@ __device__ __forceinline__ void epi_tile(const TcEpiArgs& P, TcBars* bars, const
   hook.before_stores();
   if (inb) {
     if (epi_planes) {
-      st_plane16(P.out_hi + poff, cs, oa);
-      if (NSPLIT == 2) st_plane16(P.out_lo + poff, cs, ob);
+      if (P.st_policy != 0) {
+        st_plane16_hint(P.out_hi + poff, cs, oa, P.st_policy);
+        if (NSPLIT == 2) st_plane16_hint(P.out_lo + poff, cs, ob, P.st_policy);
+      } else {
+        st_plane16(P.out_hi + poff, cs, oa);
+        if (NSPLIT == 2) st_plane16(P.out_lo + poff, cs, ob);
+      }
     } else {
       float* o = P.out_f32 + (P.f32_chunked ? foff : pix * NOUT + c0);
       st256(o, oa);
       st256(o + 8, ob);
     }
   }
-  if (tr != nullptr && warp == 2 && lane == 0 && 2 * it + 1 < 64) tr[128 + 2 * it + 1] = clock64();
+  if (tr != nullptr && warp == EPI0 && lane == 0 && 2 * tri + 1 < 64) tr[128 + 2 * tri + 1] = clock64();
 }
 
 }  // namespace pfnl

@@ -613,9 +613,9 @@ int tc_nonlocal(const TcWeights& tw, TcWorkspace& w, const float* tokens, const 
 
 int tc_nonlocal_tokens(const TcWeights& tw, const float* tokens, int N, int L, float* out, cudaStream_t s,
                        long long* launches, Profiler* prof) {
-  // stage-level entry (pfnl_nonlocal): grow-only scratch owned by the process (isolation benchmarks)
-  static uint8_t* scratch = nullptr;
-  static size_t cap = 0;
+  // stage-level entry (pfnl_nonlocal): grow-only scratch owned by the handle (freed by tc_destroy)
+  unsigned char*& scratch = tw.nl_scratch;
+  size_t& cap = tw.nl_scratch_cap;
   const size_t Lp = (size_t)ceil_div(L, kKT) * kKT;
   const size_t b_x = nl_x_bytes(N, Lp);
   const size_t b_g = nl_g_bytes(N, Lp);

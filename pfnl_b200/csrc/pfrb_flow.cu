@@ -23,10 +23,11 @@
 // (64 x 14 tiles = 896 exactly for conv1/conv2f; 13 items for conv10/conv2b), one weight image per CTA and
 // block (reloaded between blocks behind the first tile's patch loads), one launch instead of 40.
 //
-// Buffers: inp0 is ping-pong (block b reads A[b&1], writes A[(b+1)&1]) because conv2f(b) of a tile may run
-// before a neighbour's conv1(b) has read its halo; every other write-after-read hazard is ordered by the
-// dependency chain itself (conv1(b+1,u) waits for conv2f(b) of all neighbours of u, which have read inp1(b,u);
-// conv10(b+1,u) follows from conv2b(b, nbr(u)); conv2b(b+1,u) from conv2f(b,u,*)).
+// Buffers: every tensor is updated in place, as in the phase kernels.  The write-after-read hazards are ordered by
+// the dependency chain itself: conv2f(b,u,t) overwrites inp0(u,t), whose halo conv1(b,v,t) of the neighbours v reads -
+// but conv2f(b,u,*) waits for conv2b(b,u), which waited for conv10(b,v) of all neighbours, which waited for ALL
+// conv1(b,v,*) tiles; conv1(b+1,u) overwrites inp1(u) only after conv2f(b) of all neighbours of u (its readers);
+// conv10(b+1,u) follows from conv2b(b, nbr(u)); conv2b(b+1,u) from conv2f(b,u,*).
 // Cross-CTA visibility: writer = stores, __threadfence, fence.proxy.async, red.release.gpu; reader = ld.acquire.gpu
 // by the producer warp (lane-parallel over the <= 9 counters), fence.proxy.async, then TMA; the one generic-proxy
 // read of another CTA's data (the fp32 partial sums in the conv2f epilogue) is acquired by the reading warp and
@@ -47,16 +48,17 @@ namespace {
 
 enum FlowRole { kRoleConv1 = 0, kRoleConv10 = 1, kRoleConv2b = 2, kRoleConv2f = 3 };
 constexpr int kFlowArrivals = kTcEpiWarps;  // a finished tile adds this much to its counter
-constexpr int kFlowThreads = kTcThreads + 64;  // + dependency warp (18) + publisher warp (19)
+constexpr int kFlowThreads = kTcThreads + 64;  // 20 warps: 0 TMA, 1 MMA, 2 dependencies, 3 publisher, 4-19 epilogue
+constexpr int kFlowEpi0 = 4;                   // first epilogue warp: the epilogue is four whole warpgroups
 
 struct alignas(64) FlowParams {
-  CUtensorMap tmA[2][2];    // inp0 ping-pong buffers [buffer][plane], 3x3 halo box
+  CUtensorMap tmA[2];       // inp0 [plane], 3x3 halo box
   CUtensorMap tmB3[2];      // inp1 [plane], 3x3 halo box  (conv2 frame half)
   CUtensorMap tmB1[2];      // inp1 [plane], 1x1 box       (conv10)
   CUtensorMap tmBase[2];    // base [plane], 3x3 halo box  (conv2 base half)
   const __half* wimg[4][PFNL_NUM_BLOCK];  // [role][block]
   const float* bias[4][PFNL_NUM_BLOCK];   // [role][block] (conv2b: NULL)
-  __half* actA[2][2];
+  __half* actA[2];
   __half* actB[2];
   __half* base[2];
   float* pbase;
@@ -64,8 +66,11 @@ struct alignas(64) FlowParams {
   int* fault;        // host-mapped, see wait_timeout_trap
   int* progress;     // host-mapped progress marks, 8 ints per CTA (PFNL_FLOW_DEBUG=1), else NULL
   long long* trace;  // PFNL_TC_TRACE: per CTA {start ns, end ns, cycles, cycles spent waiting for dependencies}
+  int trace_block;   // first block of the per-tile stamps (PFNL_FLOW_TRACE_BLOCK, default 0)
+  int dbg;           // PFNL_FLOW_DBG bits (experiments, instrumented build only): 1 = no proxy fence in the publisher
+  int l2_hints;      // L2 eviction hints on (PFNL_FLOW_L2_HINTS=0 turns them off)
   int H, W, tiles_x, tiles_y, n_units;
-  int blk0, nblk, buf0;
+  int blk0, nblk;
   int n_role[4];
   float trunc_comp;
 };
@@ -138,17 +143,29 @@ __device__ __forceinline__ FlowItem flow_item(const FlowParams& p, int role, int
   const bool per_frame = role == kRoleConv1 || role == kRoleConv2f;
   f.u = per_frame ? item / kFrames : item;
   f.t = per_frame ? item - f.u * kFrames : 0;
-  f.tx = f.u % p.tiles_x;
-  const int r = f.u / p.tiles_x;
-  f.ty = r % p.tiles_y;
-  f.nimg = r / p.tiles_y;
+  // units are numbered along the SHORTER side of the tile grid first: the 3x3 neighbours of a unit are then at most
+  // min(tiles_x, tiles_y) + 1 units away, which is the look-ahead every dependency adds to the pipeline
+  if (p.tiles_y < p.tiles_x) {
+    f.ty = f.u % p.tiles_y;
+    const int r = f.u / p.tiles_y;
+    f.tx = r % p.tiles_x;
+    f.nimg = r / p.tiles_x;
+  } else {
+    f.tx = f.u % p.tiles_x;
+    const int r = f.u / p.tiles_x;
+    f.ty = r % p.tiles_y;
+    f.nimg = r / p.tiles_y;
+  }
   return f;
+}
+__device__ __forceinline__ int flow_unit(const FlowParams& p, int nimg, int ty, int tx) {
+  return p.tiles_y < p.tiles_x ? (nimg * p.tiles_x + tx) * p.tiles_y + ty : (nimg * p.tiles_y + ty) * p.tiles_x + tx;
 }
 
 // Whole producer warp: have the inputs of item f of (launch-relative) block b been published?  Lane-parallel
 // acquire loads of the <= 9 counters; on success the warp may issue the item's TMA loads.
 __device__ __forceinline__ bool flow_deps_ready(const FlowParams& p, int role, int b, const FlowItem& f, int lane,
-                                                bool blocking, long long& wait_cycles) {
+                                                bool blocking, long long& wait_cycles, long long* stamp = nullptr) {
   const int U = p.n_units;
   const int* ptr = nullptr;
   int target = 0;
@@ -165,7 +182,7 @@ __device__ __forceinline__ bool flow_deps_ready(const FlowParams& p, int role, i
   } else if (lane < 9 && (role == kRoleConv2b || b > 0)) {
     const int ty = f.ty + lane / 3 - 1, tx = f.tx + lane % 3 - 1;
     if (ty >= 0 && ty < p.tiles_y && tx >= 0 && tx < p.tiles_x) {
-      const int v = (f.nimg * p.tiles_y + ty) * p.tiles_x + tx;
+      const int v = flow_unit(p, f.nimg, ty, tx);
       if (role == kRoleConv2b) {
         ptr = p.flags + U + v;
         target = kFlowArrivals * (b + 1);
@@ -187,19 +204,25 @@ __device__ __forceinline__ bool flow_deps_ready(const FlowParams& p, int role, i
     } while (!all);
     wait_cycles += clock64() - t0;
   }
+  if (all && stamp != nullptr && lane == 0) stamp[0] = clock64();
   if (all) {
     // acquire: the polls were relaxed; one gpu-scope fence orders everything the publishers released before this
     // warp's subsequent accesses (the __all_sync above carries the other lanes' observations to every lane), the
     // proxy fence orders other CTAs' generic-proxy stores before this CTA's TMA (async proxy) reads
     __threadfence();
+    if (stamp != nullptr && lane == 0) stamp[32] = clock64();
     fence_proxy_async_all();
+    if (stamp != nullptr && lane == 0) stamp[64] = clock64();
   }
   return all;
 }
 
 // One CTA of role `role` (rank `rank` of p.n_role[role]); PC/NS/SLOT/WB describe the role's conv shape, patch ring
 // and weight-image size.
-template <int NSPLIT, class PC, int NS, int SLOT, int WB>
+// DBG = true: the instrumented build (PFNL_TC_TRACE / PFNL_FLOW_DEBUG / PFNL_FLOW_DBG): clock stamps, host-mapped
+// progress marks and the experiment switches.  Compiled separately: carrying the stamp pointers and window counters
+// through the role loops of the production kernel cost 7 % of its run time (registers; profiles/r2q_flow_ab.txt).
+template <int NSPLIT, class PC, int NS, int SLOT, int WB, bool DBG>
 __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int role, int rank) {
   using FC = FlowCfg<NSPLIT>;
   FlowCtrl* ctl = reinterpret_cast<FlowCtrl*>(smem);
@@ -251,7 +274,8 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
   const uint32_t tmem = ctl->tmem_base;
   pdl_wait();  // the previous kernel's activations are visible after this
   long long t_start = 0, c_start = 0, wait_cycles = 0;
-  int* prog = p.progress != nullptr ? p.progress + 8 * blockIdx.x : nullptr;
+  int* const prog = (DBG && p.progress != nullptr) ? p.progress + 8 * blockIdx.x : nullptr;
+  const int dbg = DBG ? p.dbg : 0;
   auto mark = [&](int slot, int state, int b, int item) {  // slot 0: producer, 4: epilogue
     if (prog != nullptr && lane == 0) {
       volatile int* q = prog;
@@ -264,10 +288,12 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
   // PFNL_TC_TRACE: rank 0 of every role stamps its first 31 tiles (clock64): [0,64) producer (inputs published,
   // loads issued), [64,128) MMA warp (data ready, issue done), [128,192) epilogue (accumulator ready, stores
   // issued), [192,256) epilogue (counter published)
-  long long* tr = (p.trace != nullptr && rank == 0) ? p.trace + 4 * 256 + role * 256 : nullptr;
+  long long* const tr = (DBG && p.trace != nullptr && rank == 0) ? p.trace + 4 * 256 + role * 512 : nullptr;
   if (tr != nullptr && tid == 0) tr[63] = clock64();
-  int ptile = 0;
-  if (p.trace != nullptr && tid == 0) {
+  // window of the stamps: tiles of this CTA from block p.trace_block on
+  const int it0 = DBG ? p.trace_block * ((n_items - rank + nr - 1) / nr) : 0;
+  int ptile = -it0;
+  if (DBG && p.trace != nullptr && tid == 0) {
     t_start = globaltimer_ns();
     c_start = clock64();
   }
@@ -282,21 +308,29 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
         int nissued = 0;
         auto seen = [&]() { return deps_seen_load(&ctl->deps_seen); };
         for (int b = 0; b < p.nblk; ++b) {
-          const int pp = (p.buf0 + b) & 1;  // inp0 buffer this block reads
-          const CUtensorMap* tm_hi = role == kRoleConv1    ? &p.tmA[pp][0]
+          const CUtensorMap* tm_hi = role == kRoleConv1    ? &p.tmA[0]
                                      : role == kRoleConv10 ? &p.tmB1[0]
                                      : role == kRoleConv2b ? &p.tmBase[0]
                                                            : &p.tmB3[0];
-          const CUtensorMap* tm_lo = role == kRoleConv1    ? &p.tmA[pp][1]
+          const CUtensorMap* tm_lo = role == kRoleConv1    ? &p.tmA[1]
                                      : role == kRoleConv10 ? &p.tmB1[1]
                                      : role == kRoleConv2b ? &p.tmBase[1]
                                                            : &p.tmB3[1];
+          // L2 eviction hints: the working set of a block (inp0 29 MB + inp1 29 MB + base/partials 8 MB at 16 clips)
+          // is about what one die's L2 keeps, and inp0 is the tensor with the long reuse distance - conv2f reads
+          // it as the residual a whole block after it was written (ncu before the hints: 29 MB of DRAM reads per
+          // block, profiles/r2o_pfrb_flow_full.txt).  inp0 is kept (evict_last: conv1's loads, conv2f's stores);
+          // the last readers of inp1 and base (conv2f, conv2b) mark their lines evict_first.
+          const uint64_t pol = !p.l2_hints ? 0ull
+                               : role == kRoleConv1 ? kL2EvictLast
+                               : role == kRoleConv10 ? 0ull
+                                                     : kL2EvictFirst;
           auto issue = [&](const FlowItem& f) {
-            if (tr != nullptr && ptile < 31) tr[2 * ptile] = clock64();
+            if (tr != nullptr && ptile >= 0 && ptile < 31) tr[2 * ptile] = clock64();
             load_tile<PC, NSPLIT, NS, SLOT>(tm_hi, tm_lo, ring, bars, rg, f.tx * 8 - PAD, f.ty * 16 - PAD,
                                             per_frame ? f.nimg * kFrames + f.t
-                                                      : f.nimg * (role == kRoleConv10 ? kFrames : 1));
-            if (tr != nullptr && ptile < 31) tr[2 * ptile + 1] = clock64();
+                                                      : f.nimg * (role == kRoleConv10 ? kFrames : 1), pol);
+            if (tr != nullptr && ptile >= 0 && ptile < 31) tr[2 * ptile + 1] = clock64();
             ++ptile;
             ++nissued;
           };
@@ -328,14 +362,14 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
                 __nanosleep(32);
                 if (clock64() - t0 > kTcWaitLimitCycles) wait_timeout_trap(p.fault, 6, b, item);
               }
-              wait_cycles += clock64() - t0;
+              if (DBG) wait_cycles += clock64() - t0;
             }
             mark(0, 2, b, item);
             issue(flow_item(p, role, item));
           }
           mark(0, 4, b, item);
         }
-        if (p.trace != nullptr) p.trace[4 * blockIdx.x + 3] = wait_cycles;
+        if (DBG && p.trace != nullptr) p.trace[4 * blockIdx.x + 3] = wait_cycles;
       }
     } else if (warp == 1) {
       // ===================== MMA issuer (converged warp) =====================
@@ -346,15 +380,16 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
         fence_after_sync();
         for (int item = rank; item < n_items; item += nr, ++it) {
           if (prog != nullptr && lane == 0) *(volatile int*)(prog + 3) = it + 1;
-          mma_tile<PC, NSPLIT, NS, SLOT, FC::TMEM_BUF_COLS, FC::CH_STRIDE>(wsm, ring, bars, tmem, rg, it, lane, tr);
+          mma_tile<PC, NSPLIT, NS, SLOT, FC::TMEM_BUF_COLS, FC::CH_STRIDE>(wsm, ring, bars, tmem, rg, it, lane,
+                                                                           it >= it0 ? tr : nullptr, it - it0);
         }
         if (b + 1 < p.nblk) {
           if (elect_one()) mma_commit(&ctl->wfree);  // arrives when every MMA issued so far has completed
           __syncwarp();
         }
       }
-    } else if (warp < 2 + kTcEpiWarps) {
-      // ===================== epilogue (warps 2..17) =====================
+    } else if (warp >= kFlowEpi0) {
+      // ===================== epilogue (warps 4..19) =====================
       int it = 0;
       U256 pre[2];
 #pragma unroll
@@ -365,24 +400,24 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
       // warps only hand the tile to the publisher warp through an mbarrier (release at CTA scope).
       TcNoHook nohook;
       for (int b = 0; b < p.nblk; ++b) {
-        const int pp = (p.buf0 + b) & 1;
         TcEpiArgs E;
         E.epi = role == kRoleConv2b ? kEpiPartialF32 : (role == kRoleConv2f ? kEpiResPlanes : kEpiActPlanes);
         E.accumulate = 0;
         E.f32_chunked = 1;
         E.coherent_pbase = 1;
         E.pbase = p.pbase;
-        E.out_hi = role == kRoleConv1 ? p.actB[0] : (role == kRoleConv10 ? p.base[0] : p.actA[pp ^ 1][0]);
-        E.out_lo = role == kRoleConv1 ? p.actB[1] : (role == kRoleConv10 ? p.base[1] : p.actA[pp ^ 1][1]);
-        E.res_hi = p.actA[pp][0];
-        E.res_lo = p.actA[pp][1];
+        E.out_hi = role == kRoleConv1 ? p.actB[0] : (role == kRoleConv10 ? p.base[0] : p.actA[0]);  // conv2f: in place
+        E.out_lo = role == kRoleConv1 ? p.actB[1] : (role == kRoleConv10 ? p.base[1] : p.actA[1]);
+        E.res_hi = p.actA[0];
+        E.res_lo = p.actA[1];
         E.out_f32 = p.pbase;
         E.H = p.H;
         E.W = p.W;
         E.trunc_comp = p.trunc_comp;
+        E.st_policy = (p.l2_hints && role == kRoleConv2f) ? kL2EvictLast : 0ull;
         for (int item = rank; item < n_items; item += nr, ++it) {
           const FlowItem f = flow_item(p, role, item);
-          if (warp == 2) mark(4, 1, b, item);
+          if (warp == kFlowEpi0) mark(4, 1, b, item);
           if (role == kRoleConv2f) {
             // the partial sums of this unit come from a conv2b CTA and are read with generic loads: wait until the
             // producer warp has acquired this item's counters (CTA-scope acquire of its count; the loads
@@ -400,20 +435,23 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
               }
             }
           }
-          epi_tile<PC, NSPLIT, FC::TMEM_BUF_COLS, FC::CH_STRIDE>(E, bars, ctl->bias[b], tmem, it, warp, lane,
+          epi_tile<PC, NSPLIT, FC::TMEM_BUF_COLS, FC::CH_STRIDE, TcNoHook, kFlowEpi0>(E, bars, ctl->bias[b], tmem, it, warp, lane,
                                                                  per_frame ? f.nimg * kFrames + f.t : f.nimg, f.nimg,
-                                                                 f.tx, f.ty, true, pre, tr, nohook);
+                                                                 f.tx, f.ty, true, pre, it >= it0 ? tr : nullptr, nohook,
+                                                                 it - it0);
           // hand the tile to the publisher warp (slot it & 1; wait until it has consumed the slot's previous tile)
           __syncwarp();
           if (lane == 0) {
+            if (tr != nullptr && it - it0 == 2) tr[480 + warp - kFlowEpi0] = clock64();
             mbar_wait(&ctl->pubfree[it & 1], ((it >> 1) & 1) ^ 1, p.fault);
             mbar_arrive(&ctl->stored[it & 1]);
+            if (tr != nullptr && it - it0 == 2) tr[496 + warp - kFlowEpi0] = clock64();
           }
-          if (warp == 2) mark(4, 3, b, item);
+          if (warp == kFlowEpi0) mark(4, 3, b, item);
         }
       }
-    } else if (warp == 2 + kTcEpiWarps) {
-      // ===================== dependency warp (warp 18) =====================
+    } else if (warp == 2) {
+      // ===================== dependency warp (warp 2) =====================
       // Walks the CTA's item sequence ahead of everybody else: lane-parallel relaxed polls of the <= 9 counters an
       // item waits for, one gpu-scope acquire fence + proxy fence per item, then the count of acquired items goes
       // to shared memory (release at CTA scope) for the TMA thread and the conv2 epilogue warps.
@@ -422,14 +460,15 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
       for (int b = 0; b < p.nblk; ++b)
         for (int item = rank; item < n_items; item += nr) {
           const FlowItem f = flow_item(p, role, item);
-          flow_deps_ready(p, role, b, f, lane, true, dummy);
+          flow_deps_ready(p, role, b, f, lane, true, dummy,
+                          (tr != nullptr && nseen >= it0 && nseen - it0 < 32) ? tr + 384 + (nseen - it0) : nullptr);
           ++nseen;
           if (lane == 0)
             deps_seen_store(&ctl->deps_seen, nseen);
           __syncwarp();
         }
     } else if (lane == 0) {
-      // ===================== publisher (warp 19, one thread) =====================
+      // ===================== publisher (warp 3, one thread) =====================
       // waits until the 16 epilogue warps have issued a tile's stores (acquire at CTA scope of their release),
       // makes them visible at gpu scope and to the async proxy, then adds the tile's arrivals to its counter.
       // One thread fences for the CTA (the cooperative-groups grid-barrier pattern); its latency stalls nobody.
@@ -443,10 +482,12 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
                                  : role == kRoleConv2b ? 2 * U + f.u
                                                        : 3 * U + f.u * kFrames + f.t);
           mbar_wait(&ctl->stored[it & 1], (it >> 1) & 1, p.fault);
-          fence_proxy_async_all();
+          if (tr != nullptr && it >= it0 && it - it0 < 64) tr[256 + it - it0] = clock64();
+          if (!(dbg & 1)) fence_proxy_async_all();
+          if (tr != nullptr && it >= it0 && it - it0 < 64) tr[320 + it - it0] = clock64();
           red_release_gpu_add(done, kFlowArrivals);  // release at gpu scope: cumulative over the epilogue warps' stores
           mbar_arrive(&ctl->pubfree[it & 1]);
-          if (tr != nullptr && it < 64) tr[192 + it] = clock64();
+          if (tr != nullptr && it >= it0 && it - it0 < 64) tr[192 + it - it0] = clock64();
         }
     }
   }
@@ -457,7 +498,7 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
   // ---- the last CTA to finish clears the counters for the next launch
   const int n_flags = 10 * p.n_units;
   if (tid == 0) {
-    if (p.trace != nullptr) {
+    if (DBG && p.trace != nullptr) {
       p.trace[4 * blockIdx.x + 0] = t_start;
       p.trace[4 * blockIdx.x + 1] = globaltimer_ns();
       p.trace[4 * blockIdx.x + 2] = clock64() - c_start;
@@ -472,7 +513,7 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
   }
 }
 
-template <int NSPLIT>
+template <int NSPLIT, bool DBG>
 __global__ void __launch_bounds__(kFlowThreads, 1) pfrb_flow_kernel(const __grid_constant__ FlowParams p) {
   using FC = FlowCfg<NSPLIT>;
   extern __shared__ uint8_t smem_raw[];
@@ -483,9 +524,9 @@ __global__ void __launch_bounds__(kFlowThreads, 1) pfrb_flow_kernel(const __grid
     ++role;
   }
   if (role == kRoleConv10)
-    flow_cta<NSPLIT, typename FC::C10, FC::NS10, FC::SLOT10, FC::W10>(p, smem, role, rank);
+    flow_cta<NSPLIT, typename FC::C10, FC::NS10, FC::SLOT10, FC::W10, DBG>(p, smem, role, rank);
   else
-    flow_cta<NSPLIT, typename FC::C3, FC::NS3, FC::SLOT3, FC::W3>(p, smem, role, rank);
+    flow_cta<NSPLIT, typename FC::C3, FC::NS3, FC::SLOT3, FC::W3, DBG>(p, smem, role, rank);
 }
 
 bool flow_tracing() {
@@ -494,7 +535,7 @@ bool flow_tracing() {
 }
 
 template <int NSPLIT>
-int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int buf0, int N, int H, int W, bool pdl,
+int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int N, int H, int W, bool pdl,
                 cudaStream_t s) {
   using FC = FlowCfg<NSPLIT>;
   FlowParams p;
@@ -503,8 +544,7 @@ int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int buf
   int r = 0;
   for (int pl = 0; pl < 2 && r == 0; ++pl) {
     const int sp = pl < NSPLIT ? pl : 0;  // fp16 mode: the lo maps alias the hi plane (never used)
-    r = make_act_tmap(&p.tmA[0][pl], w.actA[sp], images, H, W, FC::C3::BOX_W, FC::C3::BOX_H);
-    if (r == 0) r = make_act_tmap(&p.tmA[1][pl], w.actA2[sp], images, H, W, FC::C3::BOX_W, FC::C3::BOX_H);
+    r = make_act_tmap(&p.tmA[pl], w.actA[sp], images, H, W, FC::C3::BOX_W, FC::C3::BOX_H);
     if (r == 0) r = make_act_tmap(&p.tmB3[pl], w.actB[sp], images, H, W, FC::C3::BOX_W, FC::C3::BOX_H);
     if (r == 0) r = make_act_tmap(&p.tmB1[pl], w.actB[sp], images, H, W, FC::C10::BOX_W, FC::C10::BOX_H);
     if (r == 0) r = make_act_tmap(&p.tmBase[pl], w.base[sp], N, H, W, FC::C3::BOX_W, FC::C3::BOX_H);
@@ -524,8 +564,7 @@ int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int buf
     p.bias[kRoleConv2f][i] = tw.raw.conv2_b[i];
   }
   for (int pl = 0; pl < 2; ++pl) {
-    p.actA[0][pl] = (__half*)w.actA[pl];
-    p.actA[1][pl] = (__half*)w.actA2[pl];
+    p.actA[pl] = (__half*)w.actA[pl];
     p.actB[pl] = (__half*)w.actB[pl];
     p.base[pl] = (__half*)w.base[pl];
   }
@@ -541,7 +580,6 @@ int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int buf
   p.n_units = N * p.tiles_x * p.tiles_y;
   p.blk0 = blk0;
   p.nblk = nblk;
-  p.buf0 = buf0;
   p.trunc_comp = tw.trunc_comp;
   // role split of the grid ~ MMA work per block (conv1 252 : conv10 28 : conv2b 36 : conv2f 252 k-steps per
   // unit), conv10 rounded up because its tiles are fill-bound: 64 / 10 / 10 / 64 of 148
@@ -569,9 +607,12 @@ int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int buf
     return PFNL_ERR_UNSUPPORTED_ARCH;
   }
   static long long* trace_dev = nullptr;
+  p.trace_block = getenv("PFNL_FLOW_TRACE_BLOCK") != nullptr ? atoi(getenv("PFNL_FLOW_TRACE_BLOCK")) : 0;
+  p.dbg = getenv("PFNL_FLOW_DBG") != nullptr ? atoi(getenv("PFNL_FLOW_DBG")) : 0;
+  p.l2_hints = !(getenv("PFNL_FLOW_L2_HINTS") != nullptr && getenv("PFNL_FLOW_L2_HINTS")[0] == '0');
   if (flow_tracing()) {
-    if (!trace_dev) PFNL_CUDA(cudaMalloc((void**)&trace_dev, (4 * 256 + 4 * 256) * sizeof(long long)));
-    PFNL_CUDA(cudaMemsetAsync(trace_dev, 0, (4 * 256 + 4 * 256) * sizeof(long long), s));
+    if (!trace_dev) PFNL_CUDA(cudaMalloc((void**)&trace_dev, (4 * 256 + 4 * 512) * sizeof(long long)));
+    PFNL_CUDA(cudaMemsetAsync(trace_dev, 0, (4 * 256 + 4 * 512) * sizeof(long long), s));
     p.trace = trace_dev;
   }
   cudaLaunchConfig_t cfg;
@@ -589,9 +630,12 @@ int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int buf
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  PFNL_CUDA(cudaLaunchKernelEx(&cfg, pfrb_flow_kernel<NSPLIT>, p));
+  if (flow_tracing() || p.progress != nullptr || p.dbg != 0)
+    PFNL_CUDA(cudaLaunchKernelEx(&cfg, pfrb_flow_kernel<NSPLIT, true>, p));
+  else
+    PFNL_CUDA(cudaLaunchKernelEx(&cfg, pfrb_flow_kernel<NSPLIT, false>, p));
   if (flow_tracing()) {
-    static long long t[4 * 256 + 4 * 256];
+    static long long t[4 * 256 + 4 * 512];
     PFNL_CUDA(cudaStreamSynchronize(s));
     PFNL_CUDA(cudaMemcpy(t, trace_dev, sizeof(t), cudaMemcpyDeviceToHost));
     long long first = 0, last = 0;
@@ -617,7 +661,7 @@ int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int buf
         if ((t[4 * c + 1] - first) / 1e3 < emin) emin = (t[4 * c + 1] - first) / 1e3;
       }
       {
-        const long long* q = t + 4 * 256 + role * 256;
+        const long long* q = t + 4 * 256 + role * 512;
         const long long z = q[63];
         fprintf(stderr, "  %-6s rank 0, cycles since its start; producer (inputs published, loads issued):", names[role]);
         for (int i = 0; i < 16 && q[2 * i + 1]; ++i) fprintf(stderr, " (%lld,%lld)", q[2 * i] - z, q[2 * i + 1] - z);
@@ -627,6 +671,14 @@ int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int buf
         fprintf(stderr, "\n         epilogue (accumulator ready, stores issued, counter published):");
         for (int i = 0; i < 16 && q[128 + 2 * i + 1]; ++i)
           fprintf(stderr, " (%lld,%lld,%lld)", q[128 + 2 * i] - z, q[128 + 2 * i + 1] - z, q[192 + i] - z);
+        fprintf(stderr, "\n         publisher (tile stored, after proxy fence, after release-add):");
+        for (int i = 0; i < 12 && q[256 + i]; ++i)
+          fprintf(stderr, " (%lld,%lld,%lld)", q[256 + i] - z, q[320 + i] - z, q[192 + i] - z);
+        fprintf(stderr, "\n         epilogue warps 2..17, tile 2 of the window (stores issued / arrived on `stored`):");
+        for (int i = 0; i < 16; ++i) fprintf(stderr, " %lld/%lld", q[480 + i] - z, q[496 + i] - z);
+        fprintf(stderr, "\n         dependency warp (counters ok, after gpu fence, after proxy fence):");
+        for (int i = 0; i < 12 && q[384 + i]; ++i)
+          fprintf(stderr, " (%lld,%lld,%lld)", q[384 + i] - z, q[416 + i] - z, q[448 + i] - z);
         fprintf(stderr, "\n");
       }
       fprintf(stderr,
@@ -642,9 +694,13 @@ int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int buf
 
 int tc_flow_init() {
   PFNL_CUDA(tc_apply_wait_limit_from_env());
-  PFNL_CUDA(cudaFuncSetAttribute(pfrb_flow_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  PFNL_CUDA(cudaFuncSetAttribute(pfrb_flow_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  FlowCfg<1>::SMEM_BYTES));
-  PFNL_CUDA(cudaFuncSetAttribute(pfrb_flow_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  PFNL_CUDA(cudaFuncSetAttribute(pfrb_flow_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 FlowCfg<2>::SMEM_BYTES));
+  PFNL_CUDA(cudaFuncSetAttribute(pfrb_flow_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 FlowCfg<1>::SMEM_BYTES));
+  PFNL_CUDA(cudaFuncSetAttribute(pfrb_flow_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  FlowCfg<2>::SMEM_BYTES));
   return PFNL_OK;
 }
@@ -656,7 +712,7 @@ bool tc_flow_default() {
   return !off;
 }
 
-int tc_pfrb_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int buf0, int N, int H, int W, bool pdl,
+int tc_pfrb_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int N, int H, int W, bool pdl,
                  cudaStream_t s) {
   if (blk0 < 0 || nblk < 1 || blk0 + nblk > PFNL_NUM_BLOCK) {
     set_error("tc_pfrb_flow: blocks [%d,%d) out of range", blk0, blk0 + nblk);
@@ -666,8 +722,8 @@ int tc_pfrb_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int bu
     set_error("tc_pfrb_flow: dependency counters are not allocated");
     return PFNL_ERR_BAD_ARG;
   }
-  if (tw.nsplit == 2) return launch_flow<2>(tw, w, blk0, nblk, buf0, N, H, W, pdl, s);
-  return launch_flow<1>(tw, w, blk0, nblk, buf0, N, H, W, pdl, s);
+  if (tw.nsplit == 2) return launch_flow<2>(tw, w, blk0, nblk, N, H, W, pdl, s);
+  return launch_flow<1>(tw, w, blk0, nblk, N, H, W, pdl, s);
 }
 
 }  // namespace pfnl

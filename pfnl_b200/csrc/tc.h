@@ -63,6 +63,10 @@ struct TcWeights {
   void* conv0 = nullptr;  // [10 k-chunks][nsplit*64 rows][8 k] fp16, un-swizzled core matrices (conv0_tc_kernel)
   float* zero_bias = nullptr;  // [64] zeros
   bool flow = true;            // PFRB stack as the persistent dataflow kernel (pfnl_set_flow / PFNL_TC_FLOW=0: phase kernels)
+  bool pdl = true;             // programmatic dependent launch between the tensor-core kernels (off while profiling)
+  // grow-only scratch of the stage-level non-local entry (pfnl_nonlocal): operands, partials, Y
+  mutable unsigned char* nl_scratch = nullptr;
+  mutable size_t nl_scratch_cap = 0;
   float trunc_comp = 0.f;      // kappa of the TMEM truncation-bias compensation (conv_tc_dev.cuh); PFNL_TC_TRUNC_COMP
   int num_sms = 0;             // SM count of the handle's device (grid size of the persistent kernels)
   // non-local (precision 2): fp16 Wg^T image etc.
@@ -72,7 +76,6 @@ struct TcWeights {
 struct TcWorkspace {
   // activations as fp16 NHWC planes [images,H,W,64]; plane 0 = hi, plane 1 = lo (x3 mode)
   void* actA[2];   // inp0 (residual stream)
-  void* actA2[2];  // second inp0 buffer: the dataflow kernel (pfrb_flow.cu) ping-pongs between actA and actA2
   void* actB[2];   // inp1
   void* base[2];   // conv10 output [N,H,W,64]
   float* pbase;    // fp32 partial conv2 over the base half [N,H,W,64]
@@ -85,9 +88,6 @@ struct TcWorkspace {
 void tc_carve(TcWorkspace& w, int precision, int N, int H, int W, const std::function<char*(size_t)>& take);
 int tc_init(TcWeights& tw, int precision, const TcRawWeights& raw, std::vector<void*>& allocs);
 void tc_destroy(TcWeights& tw);
-// Programmatic dependent launch on/off (off while pfnl_profile brackets launches with events, so
-// that per-kernel durations do not overlap).
-void tc_set_pdl(bool on);
 
 // conv0 .. convmerge1 (model/pfnl.py:61-74): inp21 [N,H,W,21] fp32 -> merge [N,H,W,48] fp32
 int tc_trunk(const TcWeights& tw, TcWorkspace& w, int precision, const float* inp21, int N, int H, int W,
@@ -102,12 +102,12 @@ int tc_nonlocal(const TcWeights& tw, TcWorkspace& w, const float* tokens, const 
 int tc_nonlocal_tokens(const TcWeights& tw, const float* tokens, int N, int L, float* out, cudaStream_t s,
                        long long* launches, Profiler* prof);
 // The PFRB stack as one persistent dataflow kernel (pfrb_flow.cu): blocks [blk0, blk0+nblk) on the fp16 planes;
-// input in inp0 buffer `buf0` (0 = actA, 1 = actA2), output in buffer (buf0 + nblk) & 1.
+// in place on actA.
 int* tc_fault_buffer();  // api.cu: host-mapped wait-timeout record (device pointer; may be NULL)
 int tc_flow_init();
 bool tc_flow_default();                          // false with PFNL_TC_FLOW=0 in the environment
 size_t tc_flow_flag_ints(int N, int H, int W);   // ints of dependency counters the launch needs (zeroed once)
-int tc_pfrb_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int buf0, int N, int H, int W, bool pdl,
+int tc_pfrb_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int N, int H, int W, bool pdl,
                  cudaStream_t s);
 // One PFRB with fp32 frames in/out (conversion kernels around the tensor-core block).
 int tc_pfrb_fp32io(const TcWeights& tw, TcWorkspace& w, int precision, int blk, const float* frames, int N, int H,

@@ -432,9 +432,16 @@ class PFNL:
         if prefix is not None:
             names = list(_weights.variable_shapes())
             have = _tfck.list_variables(prefix)
-            tensors = _tfck.read_bundle(prefix, names + (["global_step"] if "global_step" in have else []))
-            if "global_step" in tensors:
-                self.global_step = int(tensors.pop("global_step"))
+            # the reference's step counter is an unnamed tf.Variable(initial_value=0) (pfnl.py:152): it sits in its
+            # checkpoints under the key 'Variable' (int32); 'global_step' is what older saves of this class wrote
+            step_key = next((k for k in ("Variable", "global_step") if k in have), None)
+            tensors = _tfck.read_bundle(prefix, names + ([step_key] if step_key else []))
+            if step_key is not None:
+                self.global_step = int(np.asarray(tensors.pop(step_key)).reshape(-1)[0])
+            else:  # base_model.py:227 names the files VSR-<step>
+                tail = os.path.basename(prefix).rsplit("-", 1)[-1]
+                if tail.isdigit():
+                    self.global_step = int(tail)
             self.load_weights(tensors)
             print(" [*] Reading checkpoints...{} Success".format(os.path.basename(prefix)))
             return True
@@ -447,15 +454,18 @@ class PFNL:
         return False
 
     def save(self, checkpoint_dir=None, step=None):
-        """base_model.py:223-229: `<dir>/VSR-<step>.{index,data-00000-of-00001}` + `<dir>/checkpoint`,
-        in TensorFlow's V2 format so that the reference's own `load` can restore it."""
+        """base_model.py:223-229: `<dir>/VSR-<step>.{index,data-00000-of-00001}` + `<dir>/checkpoint`, in
+        TensorFlow's V2 format.  Holds the `nlvsr/*` model variables and the step counter as int32 under 'Variable'
+        (the name the reference's unnamed counter gets, pfnl.py:152).  That is what the reference's inference-time
+        Saver restores (test_video_* build a Saver over the model variables only); its train-time restore also
+        expects the Adam slot variables, which an inference-only library does not have - not compatible with that."""
         d = checkpoint_dir or self.save_dir
         step = self.global_step if step is None else int(step)
         os.makedirs(d, exist_ok=True)
         if self._weights is None:
             self._weights = _weights.xavier_init()
         tensors = dict(self._weights)
-        tensors["global_step"] = np.array(step, np.int64)
+        tensors["Variable"] = np.array(step, np.int32)
         name = "VSR-{}".format(step)
         _tfck.write_bundle(join(d, name), tensors)
         _tfck.write_checkpoint_state(d, name)

@@ -149,6 +149,15 @@ def test_pfnl_load_and_save_like_base_model(tmp_path, capsys, built_lib):
     assert m2.load(str(tmp_path / "resaved")) and m2.global_step == 5000
     for k, v in w.items():
         assert np.array_equal(m2._weights[k], v)
+    # the re-saved checkpoint names the step like the reference's unnamed counter does (pfnl.py:152): 'Variable', int32
+    lv = T.list_variables(out)
+    assert lv["Variable"] == (np.int32, ()) and "global_step" not in lv
+    # a reference-written checkpoint with neither key: the step comes from the VSR-<step> file name
+    (tmp_path / "nostep").mkdir()
+    T.write_bundle(str(tmp_path / "nostep" / "VSR-777"), w)
+    T.write_checkpoint_state(str(tmp_path / "nostep"), "VSR-777")
+    m3 = PFNL()
+    assert m3.load(str(tmp_path / "nostep")) and m3.global_step == 777
     # a checkpoint that lacks a model variable is an error, not a silent partial restore
     bad = {k: v for k, v in w.items() if k != "nlvsr/conv2_7/bias"}
     (tmp_path / "bad").mkdir()
