@@ -628,7 +628,7 @@ __global__ void __launch_bounds__(128) conv0_tc_kernel(const float* __restrict__
       __half* pl = reinterpret_cast<__half*>(&ol);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float v = __uint_as_float(d0[j]) * comp;
+        float v = __fmul_rn(__uint_as_float(d0[j]), comp);
         if (NSPLIT == 2) v = fmaf(__uint_as_float(d1[j]), 1.f / 2048.f, v);
         v = lrelu(v + bias_sm[c0 + j]);
         if (NSPLIT == 2)

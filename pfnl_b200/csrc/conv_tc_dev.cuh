@@ -121,6 +121,9 @@ __device__ __forceinline__ long long globaltimer_ns() {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// generic <-> async proxy ordering for GLOBAL memory only (the dataflow kernel's cross-CTA hand-over: stores of one
+// CTA, TMA loads of another); does not have to drain the shared-memory side
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // Whole weight image: linear bulk copies L2 -> smem (the image is stored pre-swizzled, UMMA-ready).
 template <int W_BYTES>
@@ -364,36 +367,30 @@ __device__ __forceinline__ void epi_tile(const TcEpiArgs& P, TcBars* bars, const
     // chain c: D0 at c*CH_STRIDE, D1 (split mode) at c*CH_STRIDE + NOUT.  Chains are summed in
     // fp32 round-to-nearest here; D1 carries the 2^-11-scaled cross terms.
     const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + buf * TMEM_BUF_COLS + c0;
-    // (two rounds of loads - D0 chains, then D1 chains - instead of one: 32 fewer live registers at the peak; the
-    //  epilogue warps run at the 96-register cap of a 640-thread CTA and spilled with all four slices in flight)
+    uint32_t d0[NCH][16], d1[NSPLIT == 2 ? NCH : 1][16];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      tmem_ld_32x32b_x16(t0 + c * CH_STRIDE, d0[c]);
+      if (NSPLIT == 2) tmem_ld_32x32b_x16(t0 + c * CH_STRIDE + NOUT, d1[c]);
+    }
+    tmem_ld_wait();
     float comp[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) comp[c] = 1.f + P.trunc_comp * (float)(tc_chain_len<PC>(c) + 1) * 1.1920929e-7f;
-    {
-      uint32_t d0[NCH][16];
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x16(t0 + c * CH_STRIDE, d0[c]);
-      tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) {
+      // __fmul_rn: never contracted with a later add into an FMA - the phase kernels and the dataflow kernel inline
+      // this code in different contexts and must round identically (they are compared bit for bit)
+      float a = __fmul_rn(__uint_as_float(d0[0][j]), comp[0]);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float a = __uint_as_float(d0[0][j]) * comp[0];
-#pragma unroll
-        for (int c = 1; c < NCH; ++c) a = fmaf(__uint_as_float(d0[c][j]), comp[c], a);
-        v[j] = a;
-      }
-    }
-    if (NSPLIT == 2) {
-      uint32_t d1[NCH][16];
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x16(t0 + c * CH_STRIDE + NOUT, d1[c]);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int c = 1; c < NCH; ++c) a = fmaf(__uint_as_float(d0[c][j]), comp[c], a);
+      if (NSPLIT == 2) {
         float b = __uint_as_float(d1[0][j]);
 #pragma unroll
         for (int c = 1; c < NCH; ++c) b += __uint_as_float(d1[c][j]);
-        v[j] = fmaf(b, 1.f / 2048.f, v[j]);
+        a = fmaf(b, 1.f / 2048.f, a);
       }
+      v[j] = a;
     }
   }
   // this warp's tcgen05.ld are complete: hand the TMEM buffer back before the global stores
