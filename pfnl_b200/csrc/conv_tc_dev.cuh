@@ -134,23 +134,19 @@ __device__ __forceinline__ void load_weights(uint8_t* wsm, const __half* wimg, u
   }
 }
 
-// 4 x 16-byte loads that bypass the (non-coherent) L1: data another CTA of the SAME launch has written
+// 2 x 32-byte loads that bypass the (non-coherent) L1: data another CTA of the SAME launch has written
+// (LDG.E.ENL2.256.STRONG.GPU: one full sector per lane and instruction - as four 16-byte loads the same 64 bytes
+// cost every conv2 tile 1.1 K cycles, profiles/r2z_epi_parts.txt)
 __device__ __forceinline__ void ld256x2_coherent(const float* p, U256& a, U256& b) {
-  asm volatile("ld.relaxed.gpu.global.v4.b32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(a.w[0]), "=r"(a.w[1]), "=r"(a.w[2]), "=r"(a.w[3])
+  asm volatile("ld.relaxed.gpu.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.w[0]), "=r"(a.w[1]), "=r"(a.w[2]), "=r"(a.w[3]), "=r"(a.w[4]), "=r"(a.w[5]), "=r"(a.w[6]),
+                 "=r"(a.w[7])
                : "l"(p)
                : "memory");
-  asm volatile("ld.relaxed.gpu.global.v4.b32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(a.w[4]), "=r"(a.w[5]), "=r"(a.w[6]), "=r"(a.w[7])
-               : "l"(p + 4)
-               : "memory");
-  asm volatile("ld.relaxed.gpu.global.v4.b32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(b.w[0]), "=r"(b.w[1]), "=r"(b.w[2]), "=r"(b.w[3])
+  asm volatile("ld.relaxed.gpu.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(b.w[0]), "=r"(b.w[1]), "=r"(b.w[2]), "=r"(b.w[3]), "=r"(b.w[4]), "=r"(b.w[5]), "=r"(b.w[6]),
+                 "=r"(b.w[7])
                : "l"(p + 8)
-               : "memory");
-  asm volatile("ld.relaxed.gpu.global.v4.b32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(b.w[4]), "=r"(b.w[5]), "=r"(b.w[6]), "=r"(b.w[7])
-               : "l"(p + 12)
                : "memory");
 }
 
@@ -200,11 +196,13 @@ __device__ __forceinline__ constexpr int tc_chain_len(int c) {
 // of stage s = ic0 + s; (x0, y0) = top-left pixel of the halo patch (may be negative: zero fill = 'same' padding).
 template <class PC, int NSPLIT, int NS, int SLOT_BYTES>
 __device__ __forceinline__ void load_tile(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, uint8_t* ring,
-                                          TcBars* bars, TcRing& rg, int x0, int y0, int ic0, uint64_t l2_policy = 0) {
+                                          TcBars* bars, TcRing& rg, int x0, int y0, int ic0, uint64_t l2_policy = 0,
+                                          long long* ts = nullptr) {
   for (int s = 0; s < PC::NSRC; ++s) {
 #pragma unroll
     for (int pl = 0; pl < NSPLIT; ++pl) {  // hi plane first (consumed first), then lo
       mbar_wait(&bars->empty[rg.sl], rg.ph ^ 1);
+      if (ts != nullptr && s == 0) ts[pl] = clock64();  // (trace) slot free: this load goes out now
       mbar_arrive_expect_tx(&bars->full[rg.sl], PC::PATCH_BYTES);
       if (l2_policy != 0)
         tma_load_4d_hint(ring + rg.sl * SLOT_BYTES, pl == 1 ? tm_lo : tm_hi, &bars->full[rg.sl], x0 * 8, y0, 0, ic0 + s,
@@ -223,7 +221,7 @@ __device__ __forceinline__ void load_tile(const CUtensorMap* tm_hi, const CUtens
 //   tr: clock stamps of the traced CTA (or NULL), tri: index of this tile in the trace window
 template <class PC, int NSPLIT, int NS, int SLOT_BYTES, int TMEM_BUF_COLS, int CH_STRIDE>
 __device__ __forceinline__ void mma_tile(uint8_t* wsm, uint8_t* ring, TcBars* bars, uint32_t tmem, TcRing& rg, int it,
-                                         int lane, long long* tr, int tri) {
+                                         int lane, long long* tr, int tri, long long* ts = nullptr) {
   constexpr int KS = PC::KS, NSRC = PC::NSRC, NOUT = PC::NOUT, NCH = PC::NCH, TAPS = PC::TAPS;
   constexpr int TAP_BYTES = NSPLIT * PC::WT_BYTES;
   constexpr uint32_t idesc_lo = make_idesc_f16(128, NOUT);           // A_lo x W_hi          -> D1
@@ -234,8 +232,10 @@ __device__ __forceinline__ void mma_tile(uint8_t* wsm, uint8_t* ring, TcBars* ba
   constexpr uint32_t SUB_A = PC::BOX_W * PC::BOX_H * 16;  // bytes per sub-patch
   const uint64_t wd = make_sdesc_sw128(smem_u32(wsm), 1024, 0);
   const int buf = it & 1;
+  if (ts != nullptr && lane == 0) ts[2] = clock64();
   mbar_wait(&bars->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
   fence_after_sync();
+  if (ts != nullptr && lane == 0) ts[3] = clock64();
   const uint32_t dbase = tmem + buf * TMEM_BUF_COLS;
   uint32_t accmask = 0;  // bit c: chain c's block [D0|D1] has been written in this tile
   for (int s = 0; s < NSRC; ++s) {
@@ -273,8 +273,10 @@ __device__ __forceinline__ void mma_tile(uint8_t* wsm, uint8_t* ring, TcBars* ba
     if (NSPLIT == 2) {
       // ---- lo-plane pass: D1 of chain 0 += A_lo x W_hi (chain 0 was initialised by the hi pass:
       //      tap 0 / source 0 always belongs to chain 0), so this always accumulates
+      if (ts != nullptr && lane == 0 && s == 0) ts[4] = clock64();
       mbar_wait(&bars->full[rg.sl], rg.ph);
       fence_after_sync();
+      if (ts != nullptr && lane == 0 && s == 0) ts[5] = clock64();
       const uint64_t ad = make_sdesc_interleave(smem_u32(ring + rg.sl * SLOT_BYTES), SUB_A, SBO_A);
       if (elect_one()) {
 #pragma unroll
@@ -310,6 +312,15 @@ __device__ __forceinline__ void mma_tile(uint8_t* wsm, uint8_t* ring, TcBars* ba
 struct TcNoHook {
   __device__ __forceinline__ void idle() {}
   __device__ __forceinline__ void before_stores() {}
+  __device__ __forceinline__ constexpr bool skip(int) const { return false; }
+};
+// (instrumented builds) leaves out parts of the epilogue to time the rest: 4 = partial-sum loads, 8 = residual loads,
+// 16 = stores.  The results are garbage.
+struct TcSkipHook {
+  int bits;
+  __device__ __forceinline__ void idle() {}
+  __device__ __forceinline__ void before_stores() {}
+  __device__ __forceinline__ bool skip(int b) const { return (bits & b) != 0; }
 };
 // EPI0 = index of the first of the 16 epilogue warps (a multiple of 2 with EPI0 % 4 == warp-quarter alignment kept by
 // `warp & 3`): 2 in the phase kernels (warps 2-17), 4 in the dataflow kernel (warps 4-19, whole warpgroups).
@@ -339,7 +350,7 @@ __device__ __forceinline__ void epi_tile(const TcEpiArgs& P, TcBars* bars, const
   for (int j = 0; j < 8; ++j) rh.w[j] = rl.w[j] = 0u;
   if (inb) {
     if (epi_res) {
-      if (load_pbase) {  // the base-half partial sums are shared by the unit's 7 frames
+      if (load_pbase && !hook.skip(4)) {  // the base-half partial sums are shared by the unit's 7 frames
         const float* pb = P.pbase + pbase_off(nimg, c0 >> 4, y, x, P.H, P.W);
         if (P.coherent_pbase) {
           ld256x2_coherent(pb, pre[0], pre[1]);
@@ -348,8 +359,10 @@ __device__ __forceinline__ void epi_tile(const TcEpiArgs& P, TcBars* bars, const
           pre[1] = ld256(pb + 8);
         }
       }
-      rh = ld_plane16(P.res_hi + poff, cs);
-      if (NSPLIT == 2) rl = ld_plane16(P.res_lo + poff, cs);
+      if (!hook.skip(8)) {
+        rh = ld_plane16(P.res_hi + poff, cs);
+        if (NSPLIT == 2) rl = ld_plane16(P.res_lo + poff, cs);
+      }
     } else if (epi_prev) {
       const float* o = P.out_f32 + (P.f32_chunked ? foff : pix * NOUT + c0);
       pre[0] = ld256(o);
@@ -443,7 +456,7 @@ __device__ __forceinline__ void epi_tile(const TcEpiArgs& P, TcBars* bars, const
     }
   }
   hook.before_stores();
-  if (inb) {
+  if (inb && !hook.skip(16)) {
     if (epi_planes) {
       if (P.st_policy != 0) {
         st_plane16_hint(P.out_hi + poff, cs, oa, P.st_policy);

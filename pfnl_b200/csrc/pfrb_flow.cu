@@ -40,6 +40,8 @@
 // kernels (tests/test_gpu_tensorcore.py::test_flow_matches_phase_kernels).
 #include <string.h>
 
+#include <type_traits>
+
 #include "conv_tc_dev.cuh"
 
 namespace pfnl {
@@ -52,6 +54,7 @@ constexpr int kFlowArrivals = kTcEpiWarps;  // a finished tile adds this much to
 // highest warp id among the eligible warps of a sub-partition (B300_MICROARCH.md): the four control warps - one per
 // sub-partition - sit above the epilogue warps, so a poll, a fence or an MMA issue never queues behind epilogue math
 // (with the control warps at ids 0-3 the same kernel measured 3 % slower, profiles/r2q_flow_ab.txt).
+constexpr int kFlowTraceLongs = 4 * 256 + 4 * 512;  // per-CTA summary + rank-0 stamps of the 4 roles
 constexpr int kFlowThreads = kTcThreads + 64;
 constexpr int kFlowEpi0 = 0;                   // first epilogue warp
 constexpr int kFlowWarpTma = 16, kFlowWarpMma = 17, kFlowWarpDep = 18, kFlowWarpPub = 19;
@@ -72,7 +75,8 @@ struct alignas(64) FlowParams {
   int* progress;     // host-mapped progress marks, 8 ints per CTA (PFNL_FLOW_DEBUG=1), else NULL
   long long* trace;  // PFNL_TC_TRACE: per CTA {start ns, end ns, cycles, cycles spent waiting for dependencies}
   int trace_block;   // first block of the per-tile stamps (PFNL_FLOW_TRACE_BLOCK, default 0)
-  int dbg;           // PFNL_FLOW_DBG bits (experiments, instrumented build only): 1 = no proxy fence in the publisher
+  int dbg;           // PFNL_FLOW_DBG bits (experiments, instrumented build only): 1 = no proxy fence in the publisher,
+                     // 2 = the dependency warp does not wait (free-running roles: timing only, results are garbage)
   int l2_hints;      // L2 eviction hints on (PFNL_FLOW_L2_HINTS=0 turns them off)
   int H, W, tiles_x, tiles_y, n_units;
   int blk0, nblk;
@@ -294,6 +298,9 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
   // loads issued), [64,128) MMA warp (data ready, issue done), [128,192) epilogue (accumulator ready, stores
   // issued), [192,256) epilogue (counter published)
   long long* const tr = (DBG && p.trace != nullptr && rank == 0) ? p.trace + 4 * 256 + role * 512 : nullptr;
+  // second stamp area of the traced CTA: 8 per tile of the window = {hi load out, lo load out, MMA warp before /
+  // after the accumulator-buffer wait, before / after the lo-plane wait}
+  long long* const tr2 = tr != nullptr ? p.trace + kFlowTraceLongs + 20 * 256 + role * 128 : nullptr;
   if (tr != nullptr && tid == 0) tr[63] = clock64();
   // window of the stamps: tiles of this CTA from block p.trace_block on
   const int it0 = DBG ? p.trace_block * ((n_items - rank + nr - 1) / nr) : 0;
@@ -334,7 +341,8 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
             if (tr != nullptr && ptile >= 0 && ptile < 31) tr[2 * ptile] = clock64();
             load_tile<PC, NSPLIT, NS, SLOT>(tm_hi, tm_lo, ring, bars, rg, f.tx * 8 - PAD, f.ty * 16 - PAD,
                                             per_frame ? f.nimg * kFrames + f.t
-                                                      : f.nimg * (role == kRoleConv10 ? kFrames : 1), pol);
+                                                      : f.nimg * (role == kRoleConv10 ? kFrames : 1), pol,
+                                            (tr2 != nullptr && ptile >= 0 && ptile < 16) ? tr2 + 8 * ptile : nullptr);
             if (tr != nullptr && ptile >= 0 && ptile < 31) tr[2 * ptile + 1] = clock64();
             ++ptile;
             ++nissued;
@@ -373,6 +381,8 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
             issue(flow_item(p, role, item));
           }
           mark(0, 4, b, item);
+          // (trace) when this CTA's producer left block b: how far the CTAs of a role drift apart
+          if (DBG && p.trace != nullptr && b < 20) p.trace[kFlowTraceLongs + 20 * blockIdx.x + b] = globaltimer_ns();
         }
         if (DBG && p.trace != nullptr) p.trace[4 * blockIdx.x + 3] = wait_cycles;
       }
@@ -386,7 +396,10 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
         for (int item = rank; item < n_items; item += nr, ++it) {
           if (prog != nullptr && lane == 0) *(volatile int*)(prog + 3) = it + 1;
           mma_tile<PC, NSPLIT, NS, SLOT, FC::TMEM_BUF_COLS, FC::CH_STRIDE>(wsm, ring, bars, tmem, rg, it, lane,
-                                                                           it >= it0 ? tr : nullptr, it - it0);
+                                                                           it >= it0 ? tr : nullptr, it - it0,
+                                                                           (tr2 != nullptr && it >= it0 && it - it0 < 16)
+                                                                               ? tr2 + 8 * (it - it0)
+                                                                               : nullptr);
         }
         if (b + 1 < p.nblk) {
           if (elect_one()) mma_commit(&ctl->wfree);  // arrives when every MMA issued so far has completed
@@ -403,7 +416,8 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
       // its counter) is NOT done here: 512 threads fencing after every tile cost 3-6 K cycles per tile (measured,
       // profiles/r2b_flow_trace_first.txt) and made the epilogue, not the MMAs, set the tile period.  The epilogue
       // warps only hand the tile to the publisher warp through an mbarrier (release at CTA scope).
-      TcNoHook nohook;
+      typename std::conditional<DBG, TcSkipHook, TcNoHook>::type nohook{};
+      if constexpr (DBG) nohook.bits = dbg;
       for (int b = 0; b < p.nblk; ++b) {
         TcEpiArgs E;
         E.epi = role == kRoleConv2b ? kEpiPartialF32 : (role == kRoleConv2f ? kEpiResPlanes : kEpiActPlanes);
@@ -440,7 +454,7 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
               }
             }
           }
-          epi_tile<PC, NSPLIT, FC::TMEM_BUF_COLS, FC::CH_STRIDE, TcNoHook, kFlowEpi0>(E, bars, ctl->bias[b], tmem, it, warp, lane,
+          epi_tile<PC, NSPLIT, FC::TMEM_BUF_COLS, FC::CH_STRIDE, decltype(nohook), kFlowEpi0>(E, bars, ctl->bias[b], tmem, it, warp, lane,
                                                                  per_frame ? f.nimg * kFrames + f.t : f.nimg, f.nimg,
                                                                  f.tx, f.ty, true, pre, it >= it0 ? tr : nullptr, nohook,
                                                                  it - it0);
@@ -465,8 +479,9 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
       for (int b = 0; b < p.nblk; ++b)
         for (int item = rank; item < n_items; item += nr) {
           const FlowItem f = flow_item(p, role, item);
-          flow_deps_ready(p, role, b, f, lane, true, dummy,
-                          (tr != nullptr && nseen >= it0 && nseen - it0 < 32) ? tr + 384 + (nseen - it0) : nullptr);
+          if (!(dbg & 2))  // (experiment) bit 2: nobody waits - every role free-runs, the results are garbage
+            flow_deps_ready(p, role, b, f, lane, true, dummy,
+                            (tr != nullptr && nseen >= it0 && nseen - it0 < 32) ? tr + 384 + (nseen - it0) : nullptr);
           ++nseen;
           if (lane == 0)
             deps_seen_store(&ctl->deps_seen, nseen);
@@ -586,15 +601,18 @@ int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int N, 
   p.blk0 = blk0;
   p.nblk = nblk;
   p.trunc_comp = tw.trunc_comp;
-  // role split of the grid ~ MMA work per block (conv1 252 : conv10 28 : conv2b 36 : conv2f 252 k-steps per
-  // unit), conv10 rounded up because its tiles are fill-bound: 64 / 10 / 10 / 64 of 148
+  // Role split of the grid.  Free-running (no dependency waits, PFNL_FLOW_DBG=2) a tile costs conv1 5.4 K, conv10
+  // 7.0 K, conv2b 5.3 K and conv2f 5.4 K cycles (profiles/r2z_flow_balance.txt): the kernel is bound by the slowest
+  // role's tiles-per-CTA x cost, not by the dependency loop.  Measured best of 148: 60 / 11 / 9 / 68 up to ~190
+  // units, 58 / 11 / 9 / 70 above (the residual reads of conv2f miss the L2 once a block's planes outgrow it).
   const int G = tw.num_sms;
-  const int n1 = G * 64 / 148;
-  const int rem = G - 2 * n1;
+  const int n10 = G * 11 / 148 > 0 ? G * 11 / 148 : 1;
+  const int n2b = G * 9 / 148 > 0 ? G * 9 / 148 : 1;
+  const int n1 = (G - n10 - n2b) * (p.n_units < 192 ? 60 : 58) / 128;
   p.n_role[kRoleConv1] = n1;
-  p.n_role[kRoleConv2f] = n1;
-  p.n_role[kRoleConv2b] = (rem + 1) / 2;
-  p.n_role[kRoleConv10] = rem - (rem + 1) / 2;
+  p.n_role[kRoleConv10] = n10;
+  p.n_role[kRoleConv2b] = n2b;
+  p.n_role[kRoleConv2f] = G - n10 - n2b - n1;
   {  // PFNL_FLOW_SPLIT="conv1,conv10,conv2b,conv2f" (CTAs per role, sum <= SM count): experiments only
     static const char* env = getenv("PFNL_FLOW_SPLIT");
     int a = 0, b = 0, c = 0, d = 0;
@@ -607,7 +625,7 @@ int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int N, 
     }
   }
   const int grid = p.n_role[0] + p.n_role[1] + p.n_role[2] + p.n_role[3];
-  if (n1 < 1 || p.n_role[kRoleConv10] < 1) {
+  if (n1 < 1 || p.n_role[kRoleConv2f] < 1) {
     set_error("pfrb flow kernel needs at least 8 SMs (device has %d)", G);
     return PFNL_ERR_UNSUPPORTED_ARCH;
   }
@@ -616,8 +634,8 @@ int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int N, 
   p.dbg = getenv("PFNL_FLOW_DBG") != nullptr ? atoi(getenv("PFNL_FLOW_DBG")) : 0;
   p.l2_hints = !(getenv("PFNL_FLOW_L2_HINTS") != nullptr && getenv("PFNL_FLOW_L2_HINTS")[0] == '0');
   if (flow_tracing()) {
-    if (!trace_dev) PFNL_CUDA(cudaMalloc((void**)&trace_dev, (4 * 256 + 4 * 512) * sizeof(long long)));
-    PFNL_CUDA(cudaMemsetAsync(trace_dev, 0, (4 * 256 + 4 * 512) * sizeof(long long), s));
+    if (!trace_dev) PFNL_CUDA(cudaMalloc((void**)&trace_dev, (kFlowTraceLongs + 20 * 256 + 4 * 128) * sizeof(long long)));
+    PFNL_CUDA(cudaMemsetAsync(trace_dev, 0, (kFlowTraceLongs + 20 * 256 + 4 * 128) * sizeof(long long), s));
     p.trace = trace_dev;
   }
   cudaLaunchConfig_t cfg;
@@ -640,7 +658,7 @@ int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int N, 
   else
     PFNL_CUDA(cudaLaunchKernelEx(&cfg, pfrb_flow_kernel<NSPLIT, false>, p));
   if (flow_tracing()) {
-    static long long t[4 * 256 + 4 * 512];
+    static long long t[kFlowTraceLongs + 20 * 256 + 4 * 128];
     PFNL_CUDA(cudaStreamSynchronize(s));
     PFNL_CUDA(cudaMemcpy(t, trace_dev, sizeof(t), cudaMemcpyDeviceToHost));
     long long first = 0, last = 0;
@@ -684,6 +702,29 @@ int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int N, 
         fprintf(stderr, "\n         dependency warp (counters ok, after gpu fence, after proxy fence):");
         for (int i = 0; i < 12 && q[384 + i]; ++i)
           fprintf(stderr, " (%lld,%lld,%lld)", q[384 + i] - z, q[416 + i] - z, q[448 + i] - z);
+        fprintf(stderr, "\n");
+      }
+      if (getenv("PFNL_FLOW_TRACE_CTAS") != nullptr) {
+        const long long* q2 = t + kFlowTraceLongs + 20 * 256 + role * 128;
+        const long long z = (t + 4 * 256 + role * 512)[63];
+        fprintf(stderr, "         loads (hi out, lo out) | mma warp (tile begin, accumulator free, lo wait begin, lo there):");
+        for (int i = 0; i < 16 && q2[8 * i + 3]; ++i)
+          fprintf(stderr, " (%lld,%lld|%lld,%lld,%lld,%lld)", q2[8 * i] - z, q2[8 * i + 1] - z, q2[8 * i + 2] - z,
+                  q2[8 * i + 3] - z, q2[8 * i + 4] - z, q2[8 * i + 5] - z);
+        fprintf(stderr, "\n");
+        // per block: when the first / the last CTA of the role left it (us since the first CTA started)
+        fprintf(stderr, "         producers left block b at (first, last CTA) us:");
+        for (int b = 0; b < nblk && b < 20; ++b) {
+          double lo = 1e30, hi = 0;
+          for (int k = c - n; k < c; ++k) {
+            const double v = (t[kFlowTraceLongs + 20 * k + b] - first) / 1e3;
+            if (v < lo) lo = v;
+            if (v > hi) hi = v;
+          }
+          fprintf(stderr, " %d:(%.0f,%.0f)", b, lo, hi);
+        }
+        fprintf(stderr, "\n         per CTA, end of block %d (us): ", nblk / 2);
+        for (int k = c - n; k < c; ++k) fprintf(stderr, " %.0f", (t[kFlowTraceLongs + 20 * k + nblk / 2] - first) / 1e3);
         fprintf(stderr, "\n");
       }
       fprintf(stderr,

@@ -14,14 +14,15 @@ def one():
     from pfnl_b200 import Engine, weights as WT
     e = Engine(WT.xavier_init(), 0, os.environ.get("SWEEP_PREC", "fp16x3"), graphs=True)
     n, size = int(os.environ.get("SWEEP_N", "16")), int(os.environ.get("SWEEP_SIZE", "32"))
-    x = torch.rand(n, 7, size, size, 3, device="cuda")
-    out = torch.empty(n, 1, 4 * size, 4 * size, 3, device="cuda")
+    h, w = int(os.environ.get("SWEEP_H", size)), int(os.environ.get("SWEEP_W", size))
+    x = torch.rand(n, 7, h, w, 3, device="cuda")
+    out = torch.empty(n, 1, 4 * h, 4 * w, 3, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for _ in range(5):
         e.forward(x, out=out)
     torch.cuda.synchronize()
     ts = []
-    for _ in range(30):
+    for _ in range(int(os.environ.get("SWEEP_ITERS", "30"))):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()

@@ -6,7 +6,8 @@ import sys
 
 import torch
 
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pfnl_b200 import Engine, weights as WT  # noqa: E402
 
 W = WT.xavier_init()
@@ -17,8 +18,10 @@ for name, (h, w) in {"vid4_calendar_144x180": (144, 180), "udm10_180x318": (180,
     x = torch.rand(1, 7, h, w, 3, device='cuda')
     ref = None
     row = {}
-    for prec in ("fp32", "fp16x3", "fp16x3_nltc", "fp16"):
-        e = Engine(W, 0, prec, graphs=True)
+    for prec in ("fp32", "fp16x3", "fp16x3:phase", "fp16x3_nltc", "fp16"):
+        e = Engine(W, 0, prec.split(":")[0], graphs=True)
+        if prec.endswith(":phase"):
+            e.set_flow(False)   # the two-launches-per-block kernels, for comparison with the dataflow kernel
         for _ in range(2):
             y = e.forward(x)
         ts = []
