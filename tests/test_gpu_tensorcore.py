@@ -204,12 +204,14 @@ def test_forward_128_fp16x3(tc_engines):
 
 # ---- the PFRB stack as one persistent dataflow kernel (csrc/pfrb_flow.cu) -----------------------------------
 @pytest.mark.parametrize("prec", ["fp16x3", "fp16"])
-@pytest.mark.parametrize("shape", [(1, 32, 32), (16, 32, 32), (2, 6, 10), (1, 34, 18), (3, 48, 40), (1, 128, 128)])
+@pytest.mark.parametrize("shape", [(1, 32, 32), (16, 32, 32), (2, 6, 10), (1, 34, 18), (3, 48, 40), (1, 128, 128),
+                                   (1, 144, 180), (40, 32, 32)])
 def test_flow_matches_phase_kernels(tc_engines, prec, shape):
     """Same per-tile arithmetic, different scheduling: the dataflow kernel (148 persistent CTAs with one role each,
     ordered by arrival counters) must reproduce the two-launches-per-block kernels bit for bit - any missed
     dependency (a tile read before its producer finished) shows up as a difference.  Shapes: fewer tiles than
-    CTAs, the bench shape, ragged borders, several tile rows/columns, config 4."""
+    CTAs, the bench shape, ragged borders, several tile rows/columns, config 4, a Vid4 frame and 40 clips (207 and
+    320 units: the role split of the larger problems, planes that outgrow the L2)."""
     n, h, w = shape
     eng = tc_engines[(prec, "A")]
     x = cu(R.make_input(n, h, w))
