@@ -604,11 +604,13 @@ int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int N, 
   // Role split of the grid.  Free-running (no dependency waits, PFNL_FLOW_DBG=2) a tile costs conv1 5.4 K, conv10
   // 7.0 K, conv2b 5.3 K and conv2f 5.4 K cycles (profiles/r2z_flow_balance.txt): the kernel is bound by the slowest
   // role's tiles-per-CTA x cost, not by the dependency loop.  Measured best of 148: 60 / 11 / 9 / 68 up to ~190
-  // units, 58 / 11 / 9 / 70 above (the residual reads of conv2f miss the L2 once a block's planes outgrow it).
+  // units (a flat optimum: 61/12/9/66 and 62/12/9/65 are within 0.3 %), 58 / 12 / 9 / 69 above (the residual reads
+  // of conv2f miss the L2 once a block's planes outgrow it).
   const int G = tw.num_sms;
-  const int n10 = G * 11 / 148 > 0 ? G * 11 / 148 : 1;
+  const bool large = p.n_units >= 192;
+  const int n10 = G * (large ? 12 : 11) / 148 > 0 ? G * (large ? 12 : 11) / 148 : 1;
   const int n2b = G * 9 / 148 > 0 ? G * 9 / 148 : 1;
-  const int n1 = (G - n10 - n2b) * (p.n_units < 192 ? 60 : 58) / 128;
+  const int n1 = large ? (G - n10 - n2b) * 58 / 127 : (G - n10 - n2b) * 60 / 128;
   p.n_role[kRoleConv1] = n1;
   p.n_role[kRoleConv10] = n10;
   p.n_role[kRoleConv2b] = n2b;
