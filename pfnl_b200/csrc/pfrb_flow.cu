@@ -17,10 +17,10 @@
 //                       half + residual           of inp1)
 //
 // (u = clip x spatial 16x8 tile, t = frame; 16 = one arrival per epilogue warp after its stores are fenced.)
-// Items are striped over the CTAs of a role (item = rank, rank + n_role, ...), every role advances through the
-// units in the same order at the same rate (~9 units per tile time at 16 clips), so the roles run a few tiles
-// apart and the next block starts while the previous one drains: no per-block fill/drain, 148 SMs busy
-// (64 x 14 tiles = 896 exactly for conv1/conv2f; 13 items for conv10/conv2b), one weight image per CTA and
+// Items are striped over the CTAs of a role across blocks (global item g = block * n_items + i goes to CTA
+// g % n_role), every role advances through the units in the same order at the same rate (~9 units per tile time at
+// 16 clips), so the roles run a few tiles apart and the next block starts while the previous one drains: no
+// per-block fill/drain, no per-block rounding of tiles per CTA, 148 SMs busy, one weight image per CTA and
 // block (reloaded between blocks behind the first tile's patch loads), one launch instead of 40.
 //
 // Buffers: every tensor is updated in place, as in the phase kernels.  The write-after-read hazards are ordered by
@@ -242,8 +242,16 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
   const int nr = p.n_role[role];
   const bool per_frame = role == kRoleConv1 || role == kRoleConv2f;
   const int n_items = per_frame ? p.n_units * kFrames : p.n_units;
-  const bool has_work = rank < n_items;
+  const bool has_work = rank < (long long)p.nblk * n_items;
   constexpr int PAD = (PC::KS - 1) / 2;
+  // The CTAs of a role take the role's items round-robin ACROSS blocks (item g = b * n_items + i goes to CTA g % nr):
+  // when n_items is not a multiple of nr the odd tiles rotate over the CTAs instead of landing on the low ranks in
+  // every block (896 tiles on 63 CTAs: 14.2 per CTA and block on average instead of 15 for ranks 0-13).
+  // first(b) = this CTA's first item of block b (>= n_items: none).
+  auto first = [&](int b) {
+    const int r = (rank - (int)(((long long)b * n_items) % nr)) % nr;
+    return r < 0 ? r + nr : r;
+  };
 
   // ---- prologue: touches only weights / biases (never written by any kernel); overlaps the previous
   //      kernel's tail under programmatic dependent launch
@@ -303,7 +311,7 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
   long long* const tr2 = tr != nullptr ? p.trace + kFlowTraceLongs + 20 * 256 + role * 128 : nullptr;
   if (tr != nullptr && tid == 0) tr[63] = clock64();
   // window of the stamps: tiles of this CTA from block p.trace_block on
-  const int it0 = DBG ? p.trace_block * ((n_items - rank + nr - 1) / nr) : 0;
+  const int it0 = DBG ? (int)(((long long)p.trace_block * n_items - rank + nr - 1) / nr) : 0;
   int ptile = -it0;
   if (DBG && p.trace != nullptr && tid == 0) {
     t_start = globaltimer_ns();
@@ -347,13 +355,13 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
             ++ptile;
             ++nissued;
           };
-          int item = rank;
+          int item = first(b);
           if (b > 0) {
             // everything that enters shared memory shares one queue: the first tile's patches go in front of the
             // weight image when its inputs are already there
             // (only when the whole tile fits the ring: the MMA warp frees no slot before the image has landed -
             //  the 14 loads of a conv10 tile would wait for each other)
-            if (PC::NSRC * NSPLIT <= NS && seen() > nissued) {
+            if (PC::NSRC * NSPLIT <= NS && item < n_items && seen() > nissued) {
               issue(flow_item(p, role, item));
               item += nr;
             }
@@ -393,7 +401,7 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
       for (int b = 0; b < p.nblk; ++b) {
         mbar_wait(&ctl->wfull, b & 1, p.fault);
         fence_after_sync();
-        for (int item = rank; item < n_items; item += nr, ++it) {
+        for (int item = first(b); item < n_items; item += nr, ++it) {
           if (prog != nullptr && lane == 0) *(volatile int*)(prog + 3) = it + 1;
           mma_tile<PC, NSPLIT, NS, SLOT, FC::TMEM_BUF_COLS, FC::CH_STRIDE>(wsm, ring, bars, tmem, rg, it, lane,
                                                                            it >= it0 ? tr : nullptr, it - it0,
@@ -434,7 +442,7 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
         E.W = p.W;
         E.trunc_comp = p.trunc_comp;
         E.st_policy = (p.l2_hints && role == kRoleConv2f) ? kL2EvictLast : 0ull;
-        for (int item = rank; item < n_items; item += nr, ++it) {
+        for (int item = first(b); item < n_items; item += nr, ++it) {
           const FlowItem f = flow_item(p, role, item);
           if (warp == kFlowEpi0) mark(4, 1, b, item);
           if (role == kRoleConv2f) {
@@ -477,7 +485,7 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
       int nseen = 0;
       long long dummy = 0;
       for (int b = 0; b < p.nblk; ++b)
-        for (int item = rank; item < n_items; item += nr) {
+        for (int item = first(b); item < n_items; item += nr) {
           const FlowItem f = flow_item(p, role, item);
           if (!(dbg & 2))  // (experiment) bit 2: nobody waits - every role free-runs, the results are garbage
             flow_deps_ready(p, role, b, f, lane, true, dummy,
@@ -495,7 +503,7 @@ __device__ __forceinline__ void flow_cta(const FlowParams& p, uint8_t* smem, int
       const int U = p.n_units;
       int it = 0;
       for (int b = 0; b < p.nblk; ++b)
-        for (int item = rank; item < n_items; item += nr, ++it) {
+        for (int item = first(b); item < n_items; item += nr, ++it) {
           const FlowItem f = flow_item(p, role, item);
           int* done = p.flags + (role == kRoleConv1    ? f.u
                                  : role == kRoleConv10 ? U + f.u
@@ -603,14 +611,14 @@ int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int N, 
   p.trunc_comp = tw.trunc_comp;
   // Role split of the grid.  Free-running (no dependency waits, PFNL_FLOW_DBG=2) a tile costs conv1 5.4 K, conv10
   // 7.0 K, conv2b 5.3 K and conv2f 5.4 K cycles (profiles/r2z_flow_balance.txt): the kernel is bound by the slowest
-  // role's tiles-per-CTA x cost, not by the dependency loop.  Measured best of 148: 60 / 11 / 9 / 68 up to ~190
-  // units (a flat optimum: 61/12/9/66 and 62/12/9/65 are within 0.3 %), 58 / 12 / 9 / 69 above (the residual reads
+  // role's tiles-per-CTA x cost, not by the dependency loop.  Measured best of 148: 62 / 12 / 9 / 65 up to ~190
+  // units (a flat optimum: 60/11/9/68 ... 63/12/9/64 are within 1.5 %), 58 / 12 / 9 / 69 above (the residual reads
   // of conv2f miss the L2 once a block's planes outgrow it).
   const int G = tw.num_sms;
   const bool large = p.n_units >= 192;
-  const int n10 = G * (large ? 12 : 11) / 148 > 0 ? G * (large ? 12 : 11) / 148 : 1;
+  const int n10 = G * 12 / 148 > 0 ? G * 12 / 148 : 1;
   const int n2b = G * 9 / 148 > 0 ? G * 9 / 148 : 1;
-  const int n1 = large ? (G - n10 - n2b) * 58 / 127 : (G - n10 - n2b) * 60 / 128;
+  const int n1 = (G - n10 - n2b) * (large ? 58 : 62) / 127;
   p.n_role[kRoleConv1] = n1;
   p.n_role[kRoleConv10] = n10;
   p.n_role[kRoleConv2b] = n2b;
