@@ -121,6 +121,9 @@ int pfnl_debug_fault(int* out4);
  * ([0..2] producer: state, block, item; [3] MMA warp: tiles issued; [4..6] epilogue: state, block, item; [7] role):
  * copies the first n ints (n <= 2048).  Slow; for post-mortems of a timed-out wait only. */
 int pfnl_debug_progress(int* out, int n);
+/* CTAs the PFRB dataflow kernel gives to conv1, conv10, conv2b, conv2f on a device of num_sms SMs for a problem of
+ * n_units (clips x 16x8 tiles); their sum is num_sms.  Host arithmetic only (no GPU needed). */
+int pfnl_debug_flow_split(int num_sms, int n_units, int* out4);
 
 /* Replaces: sess.run(SR_test, feed_dict={L_test: lr}) -> PFNL.forward, model/pfnl.py:39-80.
  *   lr_dev [N,7,H,W,3] -> sr_dev [N,1,4H,4W,3]; H and W even. */

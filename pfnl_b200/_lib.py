@@ -62,6 +62,7 @@ SYMBOLS = {
     "pfnl_set_flow": (_I, [_VP, _I]),
     "pfnl_debug_fault": (_I, [C.POINTER(C.c_int)]),
     "pfnl_debug_progress": (_I, [C.POINTER(C.c_int), _I]),
+    "pfnl_debug_flow_split": (_I, [_I, _I, C.POINTER(C.c_int)]),
     "pfnl_forward": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
     "pfnl_forward_host": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
     "pfnl_forward_host_submit": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _VP, C.POINTER(_I)]),

@@ -610,6 +610,12 @@ int pfnl_debug_progress(int* out, int n) {
   return PFNL_OK;
 }
 
+int pfnl_debug_flow_split(int num_sms, int n_units, int* out4) {
+  if (!out4 || num_sms < 8 || n_units < 1) return PFNL_ERR_BAD_ARG;
+  tc_flow_split(num_sms, n_units, out4);
+  return PFNL_OK;
+}
+
 long long pfnl_launch_count(const pfnl_handle* h) { return h ? h->launches : 0; }
 
 int pfnl_profile(pfnl_handle* h, int enable) {

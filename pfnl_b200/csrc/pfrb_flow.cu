@@ -609,20 +609,9 @@ int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int N, 
   p.blk0 = blk0;
   p.nblk = nblk;
   p.trunc_comp = tw.trunc_comp;
-  // Role split of the grid.  Free-running (no dependency waits, PFNL_FLOW_DBG=2) a tile costs conv1 5.4 K, conv10
-  // 7.0 K, conv2b 5.3 K and conv2f 5.4 K cycles (profiles/r2z_flow_balance.txt): the kernel is bound by the slowest
-  // role's tiles-per-CTA x cost, not by the dependency loop.  Measured best of 148: 62 / 12 / 9 / 65 up to ~190
-  // units (a flat optimum: 60/11/9/68 ... 63/12/9/64 are within 1.5 %), 58 / 12 / 9 / 69 above (the residual reads
-  // of conv2f miss the L2 once a block's planes outgrow it).
+  tc_flow_split(tw.num_sms, p.n_units, p.n_role);
   const int G = tw.num_sms;
-  const bool large = p.n_units >= 192;
-  const int n10 = G * 12 / 148 > 0 ? G * 12 / 148 : 1;
-  const int n2b = G * 9 / 148 > 0 ? G * 9 / 148 : 1;
-  const int n1 = (G - n10 - n2b) * (large ? 58 : 62) / 127;
-  p.n_role[kRoleConv1] = n1;
-  p.n_role[kRoleConv10] = n10;
-  p.n_role[kRoleConv2b] = n2b;
-  p.n_role[kRoleConv2f] = G - n10 - n2b - n1;
+  const int n1 = p.n_role[kRoleConv1];
   {  // PFNL_FLOW_SPLIT="conv1,conv10,conv2b,conv2f" (CTAs per role, sum <= SM count): experiments only
     static const char* env = getenv("PFNL_FLOW_SPLIT");
     int a = 0, b = 0, c = 0, d = 0;
@@ -747,6 +736,24 @@ int launch_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int N, 
 }
 
 }  // namespace
+
+// Role split of the grid: CTAs for conv1, conv10, conv2b, conv2f (sum = num_sms).  Free-running (no dependency
+// waits, PFNL_FLOW_DBG=2) a tile costs conv1 5.4 K, conv10 7.0 K, conv2b 5.3 K and conv2f 5.4 K cycles
+// (profiles/r2z_flow_balance.txt): the kernel is bound by the slowest role's tiles-per-CTA x cost, not by the
+// dependency loop.  Measured best of 148: 62 / 12 / 9 / 65 up to ~190 units (a flat optimum: 60/11/9/68 ...
+// 63/12/9/64 are within 1.5 %), 58 / 12 / 9 / 69 above (the residual reads of conv2f miss the L2 once a block's
+// planes outgrow it).  Other SM counts scale these shares; fewer than 8 SMs is refused by the launch.
+void tc_flow_split(int num_sms, int n_units, int out[4]) {
+  const int G = num_sms;
+  const bool large = n_units >= 192;
+  const int n10 = G * 12 / 148 > 0 ? G * 12 / 148 : 1;
+  const int n2b = G * 9 / 148 > 0 ? G * 9 / 148 : 1;
+  const int n1 = (G - n10 - n2b) * (large ? 58 : 62) / 127;
+  out[kRoleConv1] = n1;
+  out[kRoleConv10] = n10;
+  out[kRoleConv2b] = n2b;
+  out[kRoleConv2f] = G - n10 - n2b - n1;
+}
 
 int tc_flow_init() {
   PFNL_CUDA(tc_apply_wait_limit_from_env());

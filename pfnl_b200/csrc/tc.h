@@ -106,6 +106,7 @@ int tc_nonlocal_tokens(const TcWeights& tw, const float* tokens, int N, int L, f
 int* tc_fault_buffer();  // api.cu: host-mapped wait-timeout record (device pointer; may be NULL)
 int tc_flow_init();
 bool tc_flow_default();                          // false with PFNL_TC_FLOW=0 in the environment
+void tc_flow_split(int num_sms, int n_units, int out[4]);  // CTAs per role: conv1, conv10, conv2b, conv2f
 size_t tc_flow_flag_ints(int N, int H, int W);   // ints of dependency counters the launch needs (zeroed once)
 int tc_pfrb_flow(const TcWeights& tw, TcWorkspace& w, int blk0, int nblk, int N, int H, int W, bool pdl,
                  cudaStream_t s);

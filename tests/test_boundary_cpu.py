@@ -83,3 +83,22 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("no oracle", ""), f"{f} references the oracle"
+
+
+def test_flow_role_split_covers_the_device(built_lib):
+    """pfrb_flow.cu gives every SM exactly one persistent CTA with one role: the split must use all SMs, leave no
+    role empty, and be the measured one on a 148-SM B200 - host arithmetic, no GPU needed."""
+    from pfnl_b200 import _lib
+    lib = _lib.lib
+    out = (C.c_int * 4)()
+    for sms in list(range(8, 200)):
+        for units in (1, 8, 128, 191, 192, 480, 4000):
+            assert lib.pfnl_debug_flow_split(sms, units, out) == 0
+            n = list(out)
+            assert sum(n) == sms and min(n) >= 1, (sms, units, n)
+            assert n[0] + n[3] >= 3 * (n[1] + n[2]), (sms, units, n)  # the two 7-tiles-per-unit roles dominate
+    lib.pfnl_debug_flow_split(148, 128, out)
+    assert list(out) == [62, 12, 9, 65]
+    lib.pfnl_debug_flow_split(148, 480, out)
+    assert list(out) == [58, 12, 9, 69]
+    assert lib.pfnl_debug_flow_split(4, 128, out) != 0 and lib.pfnl_debug_flow_split(148, 0, out) != 0
