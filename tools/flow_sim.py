@@ -1,8 +1,11 @@
-"""Timing model of the PFRB dataflow kernel (pfnl_b200/csrc/pfrb_flow.cu): every CTA walks its items in order, a tile
-runs dependency poll -> TMA loads -> MMAs -> epilogue -> publication, with the per-stage latencies measured by
-tools/flow_trace.py (profiles/r2s_flow_trace_steady_state.txt).  It answers scheduling questions (role split, item
-order, look-ahead) without GPU time; it is a model, not a measurement.
-    python tools/flow_sim.py [clips] [tiles_y] [tiles_x] [--split a,b,c,d] [--order unit|round]"""
+"""Timing model of the dependency protocol of the PFRB dataflow kernel (pfnl_b200/csrc/pfrb_flow.cu): every CTA walks
+its items in order, a tile runs dependency poll -> TMA loads -> MMAs -> epilogue -> publication, with the per-stage
+latencies measured by tools/flow_trace.py (profiles/r2s_flow_trace_steady_state.txt).  It is a model, not a
+measurement - and its one result so far was a negative one worth keeping: with the traced latencies the protocol
+alone allows ~640 cycles per unit and block where the GPU needed 750-920, i.e. the kernel was NOT bound by the
+dependency loop but by the throughput of its slowest role (profiles/r2z_flow_balance.txt).  TM below are
+MMA issue times; the measured free-running cost of a tile is 5.3-5.4 K (3x3 roles) and 7.0 K (conv10).
+    python tools/flow_sim.py [clips] [tiles_y] [tiles_x] [--split a,b,c,d] [--look n] [--jitter f]"""
 import argparse
 
 ROLES = ("conv1", "conv10", "conv2b", "conv2f")
@@ -17,7 +20,7 @@ WSWAP = 3000  # weights of the next block: drain + load
 FR = 7
 
 
-def simulate(n_img, ty, tx, split, nblk=20, order="unit", look=1, verbose=False, jitter=0.0, seed=1, dynamic=False):
+def simulate(n_img, ty, tx, split, nblk=20, look=1, jitter=0.0, seed=1):
     import random
     rng = random.Random(seed)
     U = n_img * ty * tx
